@@ -1,0 +1,44 @@
+import os
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    import numpy as np
+    path = os.path.join(REPO, 'tests', 'golden', 'golden_v1.npz')
+    with np.load(path) as data:
+        return {k: data[k] for k in data.files}
+
+
+@pytest.fixture(scope='session')
+def ref_runtime():
+    """The unmodified reference CPU runtime behind the C ABI (oracle/_ref)."""
+    from oracle import ref_runtime as rr
+    if not rr.available():
+        rr.build()
+    if not rr.available():
+        pytest.skip('oracle/_ref is not built and /root/reference is absent')
+    return rr
+
+
+@pytest.fixture(scope='session')
+def cuda_runtime():
+    import ctypes
+    try:
+        ctypes.CDLL('libcuda.so.1')
+    except OSError:
+        pytest.skip('no CUDA driver')
+    from qgate_b200 import cudaruntime
+    if cudaruntime.get_api().device_count() == 0:
+        pytest.skip('no CUDA device')
+    return cudaruntime
