@@ -1,0 +1,952 @@
+/*
+ * engine.cu — host side of libqgate_b200.so: objects behind the C ABI of
+ * include/qgate_b200.h, the deferred gate queue, memory pool, readout staging.
+ *
+ * Replaces (all paths under /root/reference/qgate/simulator/src):
+ *   CUDAQubitStates.cpp / CUDAQubitProcessor.cpp / CUDAQubitsStatesGetter.cpp   the objects
+ *   MultiDeviceMemoryStore.cpp                                                   the allocator
+ *   DeviceGetStates.cu / TransferringRunner.cpp                                  readout pipeline
+ *   glue.cpp / cudaext.cpp                                                       the boundary
+ * Design differences that matter:
+ *   - apply_gate* only APPENDS to a per-qstates queue; any observer (probability, readout,
+ *     collapse, join, synchronize, pool creation) flushes it through the planner into fused
+ *     tile passes (planner.cpp, kernels_tile.cu).  The reference launches one kernel per gate.
+ *   - everything runs on one CUDA stream; the host blocks only where a value has to reach
+ *     the host (calc_probability, get_states, sample, synchronize).
+ *   - no CPU fallback of any kind: without a CUDA device every call fails with QGB_ERR_CUDA.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/qgate_b200.h"
+#include "gate_matrix.h"
+#include "kernels.h"
+#include "planner.h"
+
+namespace qgb {
+
+namespace {
+
+/* ---- errors ------------------------------------------------------------------------------ */
+
+thread_local std::string g_last_error;
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+[[noreturn]] void fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    throw Error{code, buf};
+}
+
+#define CUDA_CHECK(expr)                                                                           \
+    do {                                                                                           \
+        cudaError_t rc__ = (expr);                                                                 \
+        if (rc__ != cudaSuccess)                                                                   \
+            fail(rc__ == cudaErrorMemoryAllocation ? QGB_ERR_OOM : QGB_ERR_CUDA, "%s: %s (%s:%d)", \
+                 #expr, cudaGetErrorString(rc__), __FILE__, __LINE__);                             \
+    } while (0)
+
+#define QGB_TRY try {
+#define QGB_CATCH                                              \
+    }                                                          \
+    catch (const Error &e) {                                   \
+        g_last_error = e.msg;                                  \
+        return e.code;                                         \
+    }                                                          \
+    catch (const std::bad_alloc &) {                           \
+        g_last_error = "out of host memory";                   \
+        return QGB_ERR_OOM;                                    \
+    }                                                          \
+    catch (const std::exception &e) {                          \
+        g_last_error = e.what();                               \
+        return QGB_ERR_RUNTIME;                                \
+    }                                                          \
+    catch (...) {                                              \
+        g_last_error = "unknown C++ exception";                \
+        return QGB_ERR_RUNTIME;                                \
+    }                                                          \
+    return QGB_OK;
+
+/* ---- memory pool --------------------------------------------------------------------------
+ * Power-of-two size classes, freed blocks are cached and reused in stream order (one stream,
+ * so no cross-stream hazards).  Replaces MultiDeviceMemoryStore.cpp:46-201, which
+ * synchronises every device on every alloc / free. */
+struct MemPool {
+    std::map<size_t, std::vector<void *>> cached;
+    std::unordered_map<void *, size_t> live;
+    size_t live_bytes = 0, cached_bytes = 0;
+    int64_t budget = -1; /* memory_store_size preference; -1 = whatever the device has */
+
+    static size_t size_class(size_t bytes) {
+        size_t c = 512;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+
+    void trim() {
+        for (auto &kv : cached)
+            for (void *p : kv.second) cudaFree(p);
+        cached.clear();
+        cached_bytes = 0;
+    }
+
+    void *alloc(size_t bytes) {
+        const size_t c = size_class(bytes);
+        auto it = cached.find(c);
+        if (it != cached.end() && !it->second.empty()) {
+            void *p = it->second.back();
+            it->second.pop_back();
+            cached_bytes -= c;
+            live[p] = c;
+            live_bytes += c;
+            return p;
+        }
+        if (budget >= 0 && (int64_t)(live_bytes + c) > budget)
+            fail(QGB_ERR_OOM, "Out of device memory (memory_store_size budget of %lld bytes).",
+                 (long long)budget);
+        void *p = nullptr;
+        cudaError_t rc = cudaMalloc(&p, c);
+        if (rc != cudaSuccess) {
+            cudaGetLastError();
+            trim();
+            rc = cudaMalloc(&p, c);
+        }
+        if (rc != cudaSuccess) {
+            cudaGetLastError();
+            fail(QGB_ERR_OOM, "Out of device memory (%zu bytes requested, %zu live).", c, live_bytes);
+        }
+        live[p] = c;
+        live_bytes += c;
+        return p;
+    }
+
+    void release(void *p) {
+        if (!p) return;
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        const size_t c = it->second;
+        live.erase(it);
+        live_bytes -= c;
+        /* keep small and medium blocks; give the big ones back so another shape can use them */
+        if (c <= (size_t(1) << 28)) {
+            cached[c].push_back(p);
+            cached_bytes += c;
+        } else {
+            cudaFree(p);
+        }
+    }
+
+    void clear() {
+        trim();
+        for (auto &kv : live) cudaFree(kv.first);
+        live.clear();
+        live_bytes = 0;
+    }
+};
+
+/* ---- objects ------------------------------------------------------------------------------- */
+
+struct QStates {
+    int prec;
+    int n_lanes = -1;
+    void *d_amp = nullptr;
+    std::vector<Gate> queue;
+    size_t elem() const { return prec == QGB_PREC_FP64 ? 16 : 8; }
+    size_t bytes() const { return elem() << n_lanes; }
+};
+
+struct QProc {
+    int prec;
+};
+
+struct Getter {
+    int prec;
+};
+
+struct Pool {
+    int prec;
+    int n_lanes;
+    double *d_cum = nullptr;
+    SortedBits empty;
+};
+
+struct Options {
+    int64_t fuse = 1;
+    int64_t merge = 1;
+    int64_t tile_lanes_fp64 = 11, tile_lanes_fp32 = 12;
+    int64_t low_lanes_fp64 = 5, low_lanes_fp32 = 6;
+    int64_t max_gates_per_pass = QGB_MAX_OPS;
+    int64_t max_cost = 1 << 30;
+    int64_t lookahead = 4096;
+    int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
+};
+
+struct Engine {
+    bool initialized = false;
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    MemPool pool;
+    double *d_partials = nullptr; /* 2048 doubles + scalars */
+    double *h_scalar = nullptr;   /* pinned */
+    void *d_stage = nullptr;      /* readout staging */
+    void *h_stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    size_t stage_bytes = size_t(32) << 20;
+    Options opt;
+    qgb_stats stats;
+    std::unordered_set<QStates *> qstates;
+    std::unordered_set<QProc *> qprocs;
+    std::unordered_set<Getter *> getters;
+    std::unordered_set<Pool *> pools;
+};
+
+Engine g;
+
+void require_init() {
+    if (!g.initialized) fail(QGB_ERR_RUNTIME, "devices are not initialized (call qgb_devices_initialize).");
+}
+
+QStates *QS(qgb_handle h) {
+    QStates *p = reinterpret_cast<QStates *>(h);
+    if (!g.qstates.count(p)) fail(QGB_ERR_INVALID, "invalid qstates handle.");
+    return p;
+}
+QProc *QP(qgb_handle h) {
+    QProc *p = reinterpret_cast<QProc *>(h);
+    if (!g.qprocs.count(p)) fail(QGB_ERR_INVALID, "invalid qproc handle.");
+    return p;
+}
+Getter *QG(qgb_handle h) {
+    Getter *p = reinterpret_cast<Getter *>(h);
+    if (!g.getters.count(p)) fail(QGB_ERR_INVALID, "invalid getter handle.");
+    return p;
+}
+Pool *SP(qgb_handle h) {
+    Pool *p = reinterpret_cast<Pool *>(h);
+    if (!g.pools.count(p)) fail(QGB_ERR_INVALID, "invalid sampling pool handle.");
+    return p;
+}
+
+void check_prec(int prec) {
+    if (prec != QGB_PREC_FP64 && prec != QGB_PREC_FP32) fail(QGB_ERR_INVALID, "unknown precision.");
+}
+
+void check_allocated(const QStates *qs) {
+    if (!qs->d_amp || qs->n_lanes < 0) fail(QGB_ERR_RUNTIME, "qstates is not allocated.");
+}
+
+void check_lane(const QStates *qs, int lane) {
+    if (lane < 0 || lane >= qs->n_lanes) fail(QGB_ERR_INVALID, "lane %d out of range [0, %d).", lane, qs->n_lanes);
+}
+
+/* ---- flush: deferred queue -> kernels ------------------------------------------------------ */
+
+int min_tile_lanes(int prec) { return prec == QGB_PREC_FP64 ? 3 + 5 : 4 + 5; }
+
+template <typename real>
+void flush_tiled(QStates *qs) {
+    const bool fp32 = sizeof(real) == 4;
+    PlanConfig cfg;
+    cfg.fp32 = fp32;
+    cfg.K = fp32 ? 4 : 3;
+    cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
+    cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
+    cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
+    /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
+    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1) > (size_t)g.max_smem_optin) --cfg.T;
+    cfg.T = std::min(cfg.T, qs->n_lanes);
+    cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
+    if (cfg.T >= qs->n_lanes) cfg.L = std::min((int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64), cfg.T);
+    cfg.max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, QGB_MAX_OPS));
+    cfg.max_cost = (int)g.opt.max_cost;
+    cfg.lookahead = (int)g.opt.lookahead;
+    static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
+    PlanStats st;
+    while (!qs->queue.empty()) {
+        plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
+        if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
+        CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, g.stream));
+        g.stats.kernel_launches += 1;
+        g.stats.tile_passes += 1;
+        g.stats.gates_executed += st.gates_in_pass;
+        g.stats.pass_bytes += (int64_t)(2 * qs->bytes());
+    }
+}
+
+void flush(QStates *qs) {
+    if (qs->queue.empty()) return;
+    check_allocated(qs);
+    if (g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec)) {
+        if (qs->prec == QGB_PREC_FP64)
+            flush_tiled<double>(qs);
+        else
+            flush_tiled<float>(qs);
+    } else {
+        for (const Gate &gt : qs->queue) {
+            CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, gt.ctrl_mask,
+                                          g.stream));
+            g.stats.kernel_launches += 1;
+            g.stats.gates_executed += 1;
+        }
+        qs->queue.clear();
+    }
+}
+
+void submit_gate(QStates *qs, const double *mat8, const int *ctrl, int n_ctrl, int target) {
+    check_allocated(qs);
+    check_lane(qs, target);
+    Gate gt;
+    std::memcpy(gt.m, mat8, sizeof(gt.m));
+    gt.target = target;
+    gt.ctrl_mask = 0;
+    for (int i = 0; i < n_ctrl; ++i) {
+        check_lane(qs, ctrl[i]);
+        if (ctrl[i] == target) fail(QGB_ERR_INVALID, "control lane equals target lane.");
+        gt.ctrl_mask |= 1ull << ctrl[i];
+    }
+    enqueue_gate(qs->queue, gt, g.opt.merge != 0);
+    g.stats.gates_submitted += 1;
+    g.stats.gate_amp_updates += (int64_t)1 << (qs->n_lanes - n_ctrl);
+    if ((int64_t)qs->queue.size() >= g.opt.queue_limit) flush(qs);
+}
+
+void stream_sync() { CUDA_CHECK(cudaStreamSynchronize(g.stream)); }
+
+void free_qstates_buffer(QStates *qs) {
+    if (qs->d_amp) {
+        g.pool.release(qs->d_amp);
+        qs->d_amp = nullptr;
+    }
+    qs->queue.clear();
+}
+
+/* ---- readout helpers ------------------------------------------------------------------------ */
+
+void build_gather(GatherParams &gp, int prec, const int *lane_tables, const int *n_per,
+                  const qgb_handle *list, int n_qstates, int n_ext_lanes) {
+    if (n_qstates > QGB_MAX_QSTATES) fail(QGB_ERR_INVALID, "too many qstates (%d).", n_qstates);
+    gp.n_qstates = n_qstates;
+    const int *p = lane_tables;
+    for (int q = 0; q < n_qstates; ++q) {
+        QStates *qs = QS(list[q]);
+        check_allocated(qs);
+        if (qs->prec != prec) fail(QGB_ERR_RUNTIME, "Wrong type");
+        if (n_per[q] != qs->n_lanes)
+            fail(QGB_ERR_INVALID, "lane table of qstates %d has %d entries, expected %d.", q, n_per[q],
+                 qs->n_lanes);
+        flush(qs);
+        gp.qs[q].amp = qs->d_amp;
+        gp.qs[q].n_lanes = qs->n_lanes;
+        for (int l = 0; l < qs->n_lanes; ++l) {
+            if (p[l] < 0 || p[l] >= n_ext_lanes)
+                fail(QGB_ERR_INVALID, "external lane %d out of range [0, %d).", p[l], n_ext_lanes);
+            gp.qs[q].ext[l] = (int8_t)p[l];
+        }
+        p += n_per[q];
+    }
+}
+
+/* marginal probability vector on the device, 2^n_lanes doubles (caller releases to the pool) */
+double *device_prob_array(int prec, const int *lane_tables, const int *n_per, const qgb_handle *list,
+                          int n_qstates, int n_lanes, int n_hidden) {
+    if (n_lanes < 0 || n_hidden < 0 || n_lanes + n_hidden > QGB_MAX_LANES)
+        fail(QGB_ERR_INVALID, "bad lane counts (%d, %d).", n_lanes, n_hidden);
+    GatherParams gp;
+    build_gather(gp, prec, lane_tables, n_per, list, n_qstates, n_lanes + n_hidden);
+    /* level 0 sums at most 8 hidden lanes per thread, the rest is folded 8 lanes at a time */
+    int h0 = std::min(n_hidden, 8);
+    int rest = n_hidden - h0;
+    int64_t count = (int64_t)1 << (n_lanes + rest);
+    double *cur = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
+    CUDA_CHECK(launch_prob_array(prec, cur, gp, h0, 0, count, g.stream));
+    g.stats.kernel_launches += 1;
+    while (rest > 0) {
+        const int h = std::min(rest, 8);
+        rest -= h;
+        count = (int64_t)1 << (n_lanes + rest);
+        double *next = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
+        CUDA_CHECK(launch_reduce_groups(next, cur, h, count, g.stream));
+        g.stats.kernel_launches += 1;
+        g.pool.release(cur);
+        cur = next;
+    }
+    return cur;
+}
+
+/* device -> caller's (pageable) host buffer through two pinned staging buffers */
+void copy_to_host(void *dst, const void *d_src, size_t bytes) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+    stream_sync();
+    g.stats.d2h_bytes += (int64_t)bytes;
+}
+
+} // namespace
+
+} // namespace qgb
+
+using namespace qgb;
+
+extern "C" {
+
+const char *qgb_last_error(void) { return g_last_error.c_str(); }
+const char *qgb_backend_name(void) { return "cuda-sm_100a"; }
+int qgb_abi_version(void) { return 1; }
+
+int qgb_device_count(int *count) {
+    QGB_TRY
+    int n = 0;
+    cudaError_t rc = cudaGetDeviceCount(&n);
+    if (rc != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    QGB_CATCH
+}
+
+int qgb_devices_initialize(const int *device_ids, int n_device_ids, int max_po2idx_per_chunk,
+                           int64_t memory_store_size) {
+    QGB_TRY
+    (void)max_po2idx_per_chunk; /* one allocation per state vector: chunking is not needed */
+    if (g.initialized) fail(QGB_ERR_RUNTIME, "already initialized.");
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    if (n == 0) fail(QGB_ERR_CUDA, "no CUDA device.");
+    int dev = 0;
+    if (n_device_ids > 0)
+        dev = device_ids[0]; /* one process drives one GPU; further ids are other ranks' shards */
+    else
+        CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= n) fail(QGB_ERR_INVALID, "device id %d out of range [0, %d).", dev, n);
+    CUDA_CHECK(cudaSetDevice(dev));
+    g.device = dev;
+    CUDA_CHECK(cudaDeviceGetAttribute(&g.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&g.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
+    g.stream = g.own_stream;
+    CUDA_CHECK(tile_pass_configure(g.max_smem_optin));
+    g.pool.budget = memory_store_size;
+    CUDA_CHECK(cudaMalloc(&g.d_partials, sizeof(double) * 4096));
+    CUDA_CHECK(cudaMallocHost(&g.h_scalar, sizeof(double) * 16));
+    CUDA_CHECK(cudaMalloc(&g.d_stage, g.stage_bytes));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_CHECK(cudaMallocHost(&g.h_stage[i], g.stage_bytes));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g.stage_done[i], cudaEventDisableTiming));
+    }
+    g.initialized = true;
+    QGB_CATCH
+}
+
+int qgb_devices_clear(void) {
+    QGB_TRY
+    if (!g.initialized) return QGB_OK;
+    cudaStreamSynchronize(g.stream);
+    for (QStates *qs : g.qstates) {
+        qs->d_amp = nullptr;
+        qs->queue.clear();
+        qs->n_lanes = -1;
+    }
+    for (Pool *p : g.pools) p->d_cum = nullptr;
+    g.pool.clear();
+    cudaFree(g.d_partials);
+    cudaFreeHost(g.h_scalar);
+    cudaFree(g.d_stage);
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(g.h_stage[i]);
+        cudaEventDestroy(g.stage_done[i]);
+        g.h_stage[i] = nullptr;
+        g.stage_done[i] = nullptr;
+    }
+    g.d_partials = nullptr;
+    g.h_scalar = nullptr;
+    g.d_stage = nullptr;
+    cudaStreamDestroy(g.own_stream);
+    g.own_stream = g.stream = nullptr;
+    g.initialized = false;
+    QGB_CATCH
+}
+
+int qgb_set_stream(uint64_t cuda_stream) {
+    QGB_TRY
+    require_init();
+    stream_sync();
+    g.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : g.own_stream;
+    QGB_CATCH
+}
+
+int qgb_gate_matrix(int gate_id, const double *args, int n_args, int adjoint, double *mat8) {
+    QGB_TRY
+    const int want = gate_matrix_n_args(gate_id);
+    if (want < 0) fail(QGB_ERR_RUNTIME, "Unknown gate type.");
+    if (n_args != want) fail(QGB_ERR_INVALID, "wrong number of gate arguments.");
+    gate_matrix(gate_id, args, adjoint, mat8);
+    QGB_CATCH
+}
+
+/* ---- QubitStates ------------------------------------------------------------------------------ */
+
+int qgb_qstates_new(int prec, qgb_handle *out) {
+    QGB_TRY
+    check_prec(prec);
+    QStates *qs = new QStates();
+    qs->prec = prec;
+    g.qstates.insert(qs);
+    *out = reinterpret_cast<qgb_handle>(qs);
+    QGB_CATCH
+}
+
+int qgb_qstates_delete(qgb_handle h) {
+    QGB_TRY
+    QStates *qs = QS(h);
+    free_qstates_buffer(qs);
+    g.qstates.erase(qs);
+    delete qs;
+    QGB_CATCH
+}
+
+int qgb_qstates_deallocate(qgb_handle h) {
+    QGB_TRY
+    QStates *qs = QS(h);
+    free_qstates_buffer(qs);
+    qs->n_lanes = -1;
+    QGB_CATCH
+}
+
+int qgb_qstates_get_n_lanes(qgb_handle h, int *n_lanes) {
+    QGB_TRY
+    *n_lanes = QS(h)->n_lanes;
+    QGB_CATCH
+}
+
+/* ---- QubitProcessor ------------------------------------------------------------------------------ */
+
+int qgb_qproc_new(int prec, qgb_handle *out) {
+    QGB_TRY
+    check_prec(prec);
+    QProc *qp = new QProc();
+    qp->prec = prec;
+    g.qprocs.insert(qp);
+    *out = reinterpret_cast<qgb_handle>(qp);
+    QGB_CATCH
+}
+
+int qgb_qproc_delete(qgb_handle h) {
+    QGB_TRY
+    QProc *qp = QP(h);
+    g.qprocs.erase(qp);
+    delete qp;
+    QGB_CATCH
+}
+
+int qgb_qproc_synchronize(qgb_handle h) {
+    QGB_TRY
+    QP(h);
+    require_init();
+    for (QStates *qs : g.qstates) flush(qs);
+    stream_sync();
+    QGB_CATCH
+}
+
+int qgb_qproc_reset(qgb_handle h) {
+    QGB_TRY
+    QP(h);
+    QGB_CATCH
+}
+
+int qgb_qproc_initialize_qstates(qgb_handle qp, qgb_handle h, int n_lanes) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    if (n_lanes < 0 || n_lanes > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "n_lanes %d out of range.", n_lanes);
+    free_qstates_buffer(qs);
+    qs->n_lanes = n_lanes;
+    qs->d_amp = g.pool.alloc(qs->bytes());
+    QGB_CATCH
+}
+
+int qgb_qproc_reset_qstates(qgb_handle qp, qgb_handle h) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    qs->queue.clear();
+    CUDA_CHECK(launch_set_basis_state(qs->prec, qs->d_amp, 1ull << qs->n_lanes, 0, g.stream));
+    g.stats.kernel_launches += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_calc_probability(qgb_handle qp, qgb_handle h, int lane, double *prob) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    check_lane(qs, lane);
+    flush(qs);
+    CUDA_CHECK(launch_prob0(qs->prec, qs->d_amp, qs->n_lanes, lane, g.d_partials, g.d_partials + 2048,
+                            g.stream));
+    g.stats.kernel_launches += 2;
+    CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, g.d_partials + 2048, sizeof(double), cudaMemcpyDeviceToHost,
+                               g.stream));
+    stream_sync();
+    g.stats.d2h_bytes += sizeof(double);
+    *prob = g.h_scalar[0];
+    QGB_CATCH
+}
+
+int qgb_qproc_join(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *dst = QS(hdst);
+    check_allocated(dst);
+    if (n_src < 1 || n_src > QGB_MAX_QSTATES) fail(QGB_ERR_INVALID, "bad number of source qstates (%d).", n_src);
+    JoinParams jp;
+    jp.n_src = n_src;
+    int shift = 0;
+    for (int k = n_src - 1; k >= 0; --k) {
+        QStates *src = QS(src_list[k]);
+        check_allocated(src);
+        if (src == dst) fail(QGB_ERR_INVALID, "join destination is also a source.");
+        if (src->prec != dst->prec) fail(QGB_ERR_RUNTIME, "Wrong type");
+        flush(src);
+        jp.src[k] = src->d_amp;
+        jp.n_lanes[k] = src->n_lanes;
+        jp.shift[k] = shift;
+        shift += src->n_lanes;
+    }
+    if (n_new_lanes < 0 || shift + n_new_lanes != dst->n_lanes)
+        fail(QGB_ERR_INVALID, "join: %d source lanes + %d new lanes != %d destination lanes.", shift,
+             n_new_lanes, dst->n_lanes);
+    dst->queue.clear();
+    CUDA_CHECK(launch_join(dst->prec, dst->d_amp, dst->n_lanes, shift, jp, g.stream));
+    g.stats.kernel_launches += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_decohere(qgb_handle qp, int value, double prob, qgb_handle h, int lane) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    check_lane(qs, lane);
+    flush(qs);
+    /* CPUQubitProcessor.cpp:227,235: the factor is computed in double, then cast */
+    const double norm = (value == 0) ? 1. / std::sqrt(prob) : 1. / std::sqrt(1. - prob);
+    CUDA_CHECK(launch_decohere(qs->prec, qs->d_amp, qs->n_lanes, lane, value ? 1 : 0, norm, g.stream));
+    g.stats.kernel_launches += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_decohere_and_separate(qgb_handle qp, int value, double prob, qgb_handle h0, qgb_handle h1,
+                                    qgb_handle h, int lane) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h), *qs0 = QS(h0), *qs1 = QS(h1);
+    check_allocated(qs);
+    check_allocated(qs0);
+    check_allocated(qs1);
+    check_lane(qs, lane);
+    if (qs0->n_lanes != qs->n_lanes - 1 || qs1->n_lanes != 1)
+        fail(QGB_ERR_INVALID, "decohere_and_separate: lane counts %d -> (%d, %d).", qs->n_lanes,
+             qs0->n_lanes, qs1->n_lanes);
+    if (qs0->prec != qs->prec || qs1->prec != qs->prec) fail(QGB_ERR_RUNTIME, "Wrong type");
+    flush(qs);
+    qs0->queue.clear();
+    qs1->queue.clear();
+    const double norm = (value == 0) ? 1. / std::sqrt(prob) : 1. / std::sqrt(1. - prob);
+    CUDA_CHECK(launch_decohere_separate(qs->prec, qs0->d_amp, qs->d_amp, qs->n_lanes, lane, value ? 1 : 0,
+                                        norm, g.stream));
+    CUDA_CHECK(launch_set_basis_state(qs1->prec, qs1->d_amp, 2, value ? 1 : 0, g.stream));
+    g.stats.kernel_launches += 2;
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_reset(qgb_handle qp, qgb_handle h, int lane) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    check_lane(qs, lane);
+    flush(qs);
+    CUDA_CHECK(launch_apply_reset(qs->prec, qs->d_amp, qs->n_lanes, lane, g.stream));
+    g.stats.kernel_launches += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_gate(qgb_handle qp, const double *mat8, qgb_handle h, int lane) {
+    QGB_TRY
+    QP(qp);
+    submit_gate(QS(h), mat8, nullptr, 0, lane);
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_controlled_gate(qgb_handle qp, const double *mat8, qgb_handle h, const int *ctrl,
+                                    int n_ctrl, int target) {
+    QGB_TRY
+    QP(qp);
+    submit_gate(QS(h), mat8, ctrl, n_ctrl, target);
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_gate_typed(qgb_handle qp, int gate_id, const double *args, int n_args, int adjoint,
+                               qgb_handle h, const int *ctrl, int n_ctrl, int target) {
+    QGB_TRY
+    QP(qp);
+    const int want = gate_matrix_n_args(gate_id);
+    if (want < 0) fail(QGB_ERR_RUNTIME, "Unknown gate type.");
+    if (n_args != want) fail(QGB_ERR_INVALID, "wrong number of gate arguments.");
+    double m[8];
+    gate_matrix(gate_id, args, adjoint, m);
+    submit_gate(QS(h), m, ctrl, n_ctrl, target);
+    QGB_CATCH
+}
+
+int qgb_qproc_flush(qgb_handle qp, qgb_handle h) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    flush(QS(h));
+    QGB_CATCH
+}
+
+/* ---- QubitsStatesGetter ------------------------------------------------------------------------ */
+
+int qgb_getter_new(int prec, qgb_handle *out) {
+    QGB_TRY
+    check_prec(prec);
+    Getter *gt = new Getter();
+    gt->prec = prec;
+    g.getters.insert(gt);
+    *out = reinterpret_cast<qgb_handle>(gt);
+    QGB_CATCH
+}
+
+int qgb_getter_delete(qgb_handle h) {
+    QGB_TRY
+    Getter *gt = QG(h);
+    g.getters.erase(gt);
+    delete gt;
+    QGB_CATCH
+}
+
+int qgb_getter_get_states(qgb_handle getter, void *array, int64_t array_offset, int mathop,
+                          const int *lane_tables, const int *n_per, int64_t empty_lane_mask,
+                          const qgb_handle *qstates_list, int n_qstates, int n_ext_lanes, int64_t n_states,
+                          int64_t start, int64_t step) {
+    QGB_TRY
+    Getter *gt = QG(getter);
+    /* range checks of glue.cpp:465-478 */
+    if (n_ext_lanes < 0 || n_ext_lanes > 62) fail(QGB_ERR_INVALID, "value out of range");
+    const int64_t space = (int64_t)1 << n_ext_lanes;
+    if (start < 0 || space <= start) fail(QGB_ERR_INVALID, "value out of range");
+    const int64_t end = start + step * (n_states - 1);
+    if (end < 0 || space <= end) fail(QGB_ERR_INVALID, "value out of range");
+    if (mathop != QGB_MATHOP_NULL && mathop != QGB_MATHOP_PROB) fail(QGB_ERR_RUNTIME, "unknown math op.");
+    const size_t real_size = gt->prec == QGB_PREC_FP64 ? 8 : 4;
+    const size_t item = (mathop == QGB_MATHOP_NULL) ? 2 * real_size : real_size;
+    char *dst = static_cast<char *>(array) + array_offset * item;
+    if (n_states <= 0) return QGB_OK;
+    if (n_qstates == 0) {
+        /* no qstates at all: |0...0> (glue.cpp:481-496) — a host-side constant, no device work */
+        std::memset(dst, 0, (size_t)n_states * item);
+        if (start == 0) {
+            if (real_size == 8)
+                *reinterpret_cast<double *>(dst) = 1.;
+            else
+                *reinterpret_cast<float *>(dst) = 1.f;
+        }
+        return QGB_OK;
+    }
+    require_init();
+    GatherParams gp;
+    build_gather(gp, gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_ext_lanes);
+    /* kernel -> device staging -> pinned buffer (async) -> caller's array; the copy of chunk i to the
+     * caller overlaps the kernel + D2H of chunk i+1 */
+    const int64_t per_chunk = (int64_t)(g.stage_bytes / 2 / item);
+    int64_t done = 0;
+    int buf = 0;
+    int64_t pending_count[2] = {0, 0};
+    int64_t pending_first[2] = {0, 0};
+    auto drain = [&](int b) {
+        if (pending_count[b] == 0) return;
+        CUDA_CHECK(cudaEventSynchronize(g.stage_done[b]));
+        std::memcpy(dst + pending_first[b] * item, g.h_stage[b], (size_t)pending_count[b] * item);
+        g.stats.d2h_bytes += pending_count[b] * (int64_t)item;
+        pending_count[b] = 0;
+    };
+    while (done < n_states) {
+        const int64_t count = std::min(per_chunk, n_states - done);
+        drain(buf);
+        char *d_half = static_cast<char *>(g.d_stage) + (size_t)buf * (g.stage_bytes / 2);
+        CUDA_CHECK(launch_get_states(gt->prec, d_half, mathop, gp, (uint64_t)empty_lane_mask, done, count,
+                                     start, step, g.stream));
+        g.stats.kernel_launches += 1;
+        CUDA_CHECK(cudaMemcpyAsync(g.h_stage[buf], d_half, (size_t)count * item, cudaMemcpyDeviceToHost,
+                                   g.stream));
+        CUDA_CHECK(cudaEventRecord(g.stage_done[buf], g.stream));
+        pending_first[buf] = done;
+        pending_count[buf] = count;
+        done += count;
+        buf ^= 1;
+    }
+    drain(buf);
+    drain(buf ^ 1);
+    QGB_CATCH
+}
+
+int qgb_getter_prepare_prob_array(qgb_handle getter, void *prob, const int *lane_tables, const int *n_per,
+                                  const qgb_handle *qstates_list, int n_qstates, int n_lanes, int n_hidden) {
+    QGB_TRY
+    Getter *gt = QG(getter);
+    require_init();
+    double *d_prob = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes,
+                                       n_hidden);
+    const int64_t count = (int64_t)1 << n_lanes;
+    if (gt->prec == QGB_PREC_FP64) {
+        copy_to_host(prob, d_prob, sizeof(double) * (size_t)count);
+    } else {
+        float *d_f = static_cast<float *>(g.pool.alloc(sizeof(float) * (size_t)count));
+        CUDA_CHECK(launch_cast_from_double(gt->prec, d_f, d_prob, count, g.stream));
+        g.stats.kernel_launches += 1;
+        copy_to_host(prob, d_f, sizeof(float) * (size_t)count);
+        g.pool.release(d_f);
+    }
+    g.pool.release(d_prob);
+    QGB_CATCH
+}
+
+int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, const int *n_per,
+                                    const qgb_handle *qstates_list, int n_qstates, int n_lanes, int n_hidden,
+                                    const int *empty_lanes, int n_empty, qgb_handle *out) {
+    QGB_TRY
+    Getter *gt = QG(getter);
+    require_init();
+    if (n_empty < 0 || n_empty > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of empty lanes.");
+    double *d_prob = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes,
+                                       n_hidden);
+    const int64_t n = (int64_t)1 << n_lanes;
+    const int64_t n_blocks = (n + 4095) / 4096;
+    double *d_sums = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)(n_blocks + 1)));
+    double *d_total = d_sums + n_blocks;
+    CUDA_CHECK(launch_scan_phase1(d_prob, n, d_sums, g.stream));
+    CUDA_CHECK(launch_scan_phase2(d_sums, n_blocks, d_total, g.stream));
+    CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, d_total, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    stream_sync();
+    g.stats.kernel_launches += 2;
+    const double total = g.h_scalar[0];
+    /* CPUSamplingPool.cpp:31-34 */
+    if (!(std::fabs(total - 1.) <= 0.05)) {
+        g.pool.release(d_sums);
+        g.pool.release(d_prob);
+        fail(QGB_ERR_RUNTIME, "error in probability sum is beyond 0.05., %g.", total);
+    }
+    CUDA_CHECK(launch_scan_phase3(d_prob, n, d_sums, d_total, g.stream));
+    g.stats.kernel_launches += 1;
+    g.pool.release(d_sums); /* stream-ordered: reused only by later work on the same stream */
+    Pool *p = new Pool();
+    p->prec = gt->prec;
+    p->n_lanes = n_lanes;
+    p->d_cum = d_prob;
+    std::vector<int> sorted(empty_lanes, empty_lanes + n_empty);
+    std::sort(sorted.begin(), sorted.end());
+    p->empty.n = 0;
+    for (int v : sorted) {
+        if (v < 0 || v >= 63) fail(QGB_ERR_INVALID, "bad empty lane %d.", v);
+        p->empty.pos[p->empty.n++] = (int8_t)v;
+    }
+    g.pools.insert(p);
+    *out = reinterpret_cast<qgb_handle>(p);
+    QGB_CATCH
+}
+
+/* ---- SamplingPool ------------------------------------------------------------------------------ */
+
+int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *randnum) {
+    QGB_TRY
+    Pool *p = SP(pool);
+    require_init();
+    if (!p->d_cum) fail(QGB_ERR_RUNTIME, "sampling pool was released.");
+    if (n_samples < 0) fail(QGB_ERR_INVALID, "negative number of samples.");
+    if (n_samples == 0) return QGB_OK;
+    const size_t n = (size_t)n_samples;
+    char *d_buf = static_cast<char *>(g.pool.alloc(n * 16));
+    double *d_rand = reinterpret_cast<double *>(d_buf);
+    int64_t *d_obs = reinterpret_cast<int64_t *>(d_buf + n * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_rand, randnum, n * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_CHECK(launch_sample(p->prec, p->d_cum, p->n_lanes, d_rand, d_obs, n_samples, p->empty, g.stream));
+    CUDA_CHECK(cudaMemcpyAsync(obs, d_obs, n * 8, cudaMemcpyDeviceToHost, g.stream));
+    stream_sync();
+    g.pool.release(d_buf);
+    g.stats.kernel_launches += 1;
+    g.stats.h2d_bytes += (int64_t)n * 8;
+    g.stats.d2h_bytes += (int64_t)n * 8;
+    QGB_CATCH
+}
+
+int qgb_pool_delete(qgb_handle pool) {
+    QGB_TRY
+    Pool *p = SP(pool);
+    if (p->d_cum) g.pool.release(p->d_cum);
+    g.pools.erase(p);
+    delete p;
+    QGB_CATCH
+}
+
+/* ---- instrumentation ------------------------------------------------------------------------------ */
+
+int qgb_stats_get(qgb_stats *out) {
+    *out = g.stats;
+    return QGB_OK;
+}
+
+int qgb_stats_reset(void) {
+    std::memset(&g.stats, 0, sizeof(g.stats));
+    return QGB_OK;
+}
+
+int qgb_set_option(const char *name, int64_t value) {
+    QGB_TRY
+    const std::string k(name ? name : "");
+    if (k == "fuse") g.opt.fuse = value;
+    else if (k == "merge") g.opt.merge = value;
+    else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
+    else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;
+    else if (k == "low_lanes_fp64") g.opt.low_lanes_fp64 = value;
+    else if (k == "low_lanes_fp32") g.opt.low_lanes_fp32 = value;
+    else if (k == "low_lanes") g.opt.low_lanes_fp64 = g.opt.low_lanes_fp32 = value;
+    else if (k == "max_gates_per_pass") g.opt.max_gates_per_pass = value;
+    else if (k == "max_cost") g.opt.max_cost = value;
+    else if (k == "lookahead") g.opt.lookahead = value;
+    else if (k == "queue_limit") g.opt.queue_limit = value;
+    else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
+    QGB_CATCH
+}
+
+} // extern "C"

@@ -1,0 +1,97 @@
+/*
+ * kernels.h — launchers of the sm_100a kernels (definitions in kernels_tile.cu, kernels_ops.cu).
+ * Every launcher enqueues on `stream` and returns the cudaError_t of the launch; none of
+ * them synchronises.  `prec` is QGB_PREC_FP64 (1) or QGB_PREC_FP32 (2); amplitudes are
+ * interleaved (re, im) in that precision.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace qgb {
+
+/* maximum number of qstates multiplied together by one get_states / prob-array launch */
+#define QGB_MAX_QSTATES 40
+
+struct SortedBits {
+    int32_t n;
+    int8_t pos[QGB_MAX_LANES]; /* ascending bit positions to be skipped by the pair index */
+};
+
+/* external index -> local index of one qstates: local bit l comes from external bit ext[l] */
+struct LaneTable {
+    const void *amp;
+    int32_t n_lanes;
+    int8_t ext[QGB_MAX_LANES];
+};
+
+struct GatherParams {
+    int32_t n_qstates;
+    LaneTable qs[QGB_MAX_QSTATES];
+};
+
+/* ---- gates ----------------------------------------------------------------------- */
+template <typename real>
+cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, cudaStream_t stream);
+/* smem bytes the tile kernel needs for (T, L) */
+size_t tile_pass_smem_bytes(int prec, int T, int L);
+cudaError_t tile_pass_configure(int max_smem_optin);
+
+cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
+                               uint64_t ctrl_mask, cudaStream_t stream);
+
+/* ---- state-vector maintenance ------------------------------------------------------ */
+cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,
+                                   cudaStream_t stream);
+/* partial sums -> *d_result (double) = sum_{bit lane == 0} |a|^2; d_partials holds >= 2048 doubles */
+cudaError_t launch_prob0(int prec, const void *amp, int n_lanes, int lane, double *d_partials,
+                         double *d_result, cudaStream_t stream);
+cudaError_t launch_decohere(int prec, void *amp, int n_lanes, int lane, int value, double norm,
+                            cudaStream_t stream);
+cudaError_t launch_decohere_separate(int prec, void *dst, const void *src, int n_src_lanes, int lane,
+                                     int value, double norm, cudaStream_t stream);
+cudaError_t launch_apply_reset(int prec, void *amp, int n_lanes, int lane, cudaStream_t stream);
+
+struct JoinParams {
+    int32_t n_src;
+    const void *src[QGB_MAX_QSTATES]; /* in list order; the LAST one holds the lowest lanes */
+    int32_t shift[QGB_MAX_QSTATES];
+    int32_t n_lanes[QGB_MAX_QSTATES];
+};
+/* dst[i] = prod_k src_k[(i >> shift_k) & mask_k] for i < 2^n_product, 0 above */
+cudaError_t launch_join(int prec, void *dst, int n_dst_lanes, int n_product_lanes,
+                        const JoinParams &jp, cudaStream_t stream);
+
+/* ---- readout ------------------------------------------------------------------------ */
+/* out[j] (complex<real> for mathop 0, real for mathop 1), j in [0, count):
+ * ext = start + step * (first + j); 0 if ext & empty_mask else prod_qs op(amp_qs[perm(ext)]) */
+cudaError_t launch_get_states(int prec, void *d_out, int mathop, const GatherParams &gp,
+                              uint64_t empty_mask, int64_t first, int64_t count, int64_t start,
+                              int64_t step, cudaStream_t stream);
+/* marginal probabilities: d_out[d] (double), d in [first, first+count):
+ * sum_{h < 2^n_hidden} prod_qs |amp_qs[perm((d << n_hidden) | h)]|^2 (product in `real`, sum in double) */
+cudaError_t launch_prob_array(int prec, double *d_out, const GatherParams &gp, int n_hidden,
+                              int64_t first, int64_t count, cudaStream_t stream);
+/* d_out[j] = sum of 2^log2_group consecutive d_in values (sequential, double), j < count */
+cudaError_t launch_reduce_groups(double *d_out, const double *d_in, int log2_group, int64_t count,
+                                 cudaStream_t stream);
+/* double -> real conversion of a device array (for handing the prob array to the host) */
+cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, int64_t count,
+                                    cudaStream_t stream);
+
+/* ---- sampling pool ------------------------------------------------------------------- */
+/* in-place inclusive scan of d_prob[0..n) in double with a fixed tiling (deterministic);
+ * d_block_sums holds ceil(n / 4096) doubles; *d_total receives the grand total. */
+cudaError_t launch_scan_phase1(const double *d_prob, int64_t n, double *d_block_sums, cudaStream_t stream);
+cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d_total, cudaStream_t stream);
+/* cum[i] = (offset_block + inclusive_scan_in_block) * norm, norm = 1 / total read from *d_total */
+cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums,
+                               const double *d_total, cudaStream_t stream);
+/* obs[i] = deposit(upper_bound(cum, r_i), perm); r is cast to float first when prec is FP32
+ * (CPUSamplingPool.cpp:74) */
+cudaError_t launch_sample(int prec, const double *d_cum, int n_lanes, const double *d_rand,
+                          int64_t *d_obs, int n_samples, SortedBits empty_lanes, cudaStream_t stream);
+
+} // namespace qgb

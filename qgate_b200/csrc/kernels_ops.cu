@@ -1,0 +1,547 @@
+/*
+ * kernels_ops.cu — everything on the hot path that is not a gate (sm_100a):
+ * probability reduction, measurement collapse, separate / reset / join, amplitude and
+ * probability readout, marginal probabilities, sampling-pool scan and search.
+ *
+ * Each kernel names the reference routine whose result it reproduces.  Where the reference
+ * CPU code does a short fixed sequence of multiplications and additions (join products,
+ * readout products, |a|^2) the kernels use non-contracted arithmetic (__fmul_rn / __dmul_rn
+ * ...) in the same order, so those values are bit-identical to the reference's; reductions
+ * accumulate in double with a fixed tree (deterministic, but a different order from the
+ * reference's per-worker partial sums, CPUQubitProcessor.cpp:96-123).
+ */
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace qgb {
+
+namespace {
+
+template <typename real> struct Cplx;
+template <> struct Cplx<float> { typedef float2 type; };
+template <> struct Cplx<double> { typedef double2 type; };
+
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+/* std::complex product as the reference's compiler evaluates it: (ac - bd, ad + bc) */
+template <typename C> __device__ __forceinline__ C cmul_exact(C a, C b) {
+    C o;
+    o.x = sub_rn(mul_rn(a.x, b.x), mul_rn(a.y, b.y));
+    o.y = add_rn(mul_rn(a.x, b.y), mul_rn(a.y, b.x));
+    return o;
+}
+template <typename C> __device__ __forceinline__ auto abs2_exact(C a) -> decltype(a.x) {
+    return add_rn(mul_rn(a.x, a.x), mul_rn(a.y, a.y));
+}
+
+__device__ __forceinline__ uint64_t insert_zero(uint64_t idx, int pos) {
+    const uint64_t lo = idx & ((1ull << pos) - 1ull);
+    return ((idx - lo) << 1) | lo;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* sum over the block, fixed tree; valid in thread 0 */
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double warp_part[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads(); /* protect warp_part from a previous use */
+    if (lane == 0) warp_part[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? warp_part[threadIdx.x] : 0.;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+
+/* ---- reset to a basis state (CPUQubitProcessor.cpp:61-73) ----------------------------- */
+template <typename real>
+__global__ void set_one_kernel(typename Cplx<real>::type *amp, uint64_t one_at) {
+    amp[one_at].x = (real)1;
+    amp[one_at].y = (real)0;
+}
+
+/* ---- P(lane == 0) (CPUQubitProcessor.cpp:75-125; incumbent DeviceSum.cuh:7-39) ----------- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+prob0_kernel(const typename Cplx<real>::type *__restrict__ amp, uint64_t n_half, int lane,
+             double *__restrict__ partials) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t lowmask = (1ull << lane) - 1ull;
+    double acc0 = 0., acc1 = 0., acc2 = 0., acc3 = 0.;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n_half; i += 4 * stride) {
+        typename Cplx<real>::type v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t j = i + u * stride;
+            v[u] = amp[((j & ~lowmask) << 1) | (j & lowmask)];
+        }
+        acc0 += (double)v[0].x * v[0].x + (double)v[0].y * v[0].y;
+        acc1 += (double)v[1].x * v[1].x + (double)v[1].y * v[1].y;
+        acc2 += (double)v[2].x * v[2].x + (double)v[2].y * v[2].y;
+        acc3 += (double)v[3].x * v[3].x + (double)v[3].y * v[3].y;
+    }
+    for (; i < n_half; i += stride) {
+        const typename Cplx<real>::type v = amp[((i & ~lowmask) << 1) | (i & lowmask)];
+        acc0 += (double)v.x * v.x + (double)v.y * v.y;
+    }
+    const double s = block_sum((acc0 + acc1) + (acc2 + acc3));
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024)
+final_sum_kernel(const double *__restrict__ partials, int n, double *__restrict__ result) {
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partials[i];
+    const double s = block_sum(acc);
+    if (threadIdx.x == 0) *result = s;
+}
+
+/* ---- measurement collapse (CPUQubitProcessor.cpp:217-246) --------------------------------- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+decohere_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_amps, int lane, int value,
+                real norm) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_amps; i += stride) {
+        typename Cplx<real>::type v = amp[i];
+        if ((int)((i >> lane) & 1ull) == value) {
+            v.x = mul_rn(v.x, norm);
+            v.y = mul_rn(v.y, norm);
+        } else {
+            v.x = (real)0;
+            v.y = (real)0;
+        }
+        amp[i] = v;
+    }
+}
+
+/* ---- collapse + remove the lane (CPUQubitProcessor.cpp:248-284) ---------------------------- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+decohere_separate_kernel(typename Cplx<real>::type *__restrict__ dst,
+                         const typename Cplx<real>::type *__restrict__ src, uint64_t n_dst, int lane,
+                         int value, real norm) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t bit = (uint64_t)value << lane;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += stride) {
+        typename Cplx<real>::type v = src[insert_zero(i, lane) | bit];
+        v.x = mul_rn(norm, v.x);
+        v.y = mul_rn(norm, v.y);
+        dst[i] = v;
+    }
+}
+
+/* ---- reset of a lane measured as 1 (CPUQubitProcessor.cpp:286-305) -------------------------- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+apply_reset_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_half, int lane) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    typename Cplx<real>::type zero;
+    zero.x = (real)0;
+    zero.y = (real)0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_half; i += stride) {
+        const uint64_t i0 = insert_zero(i, lane), i1 = i0 | (1ull << lane);
+        amp[i0] = amp[i1];
+        amp[i1] = zero;
+    }
+}
+
+/* ---- join = Kronecker product + zero padding (CPUQubitProcessor.cpp:129-213) --------------- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+join_kernel(typename Cplx<real>::type *__restrict__ dst, uint64_t n_dst, uint64_t n_product,
+            const __grid_constant__ JoinParams jp) {
+    typedef typename Cplx<real>::type cplx;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += stride) {
+        cplx v;
+        if (i < n_product) {
+            const int last = jp.n_src - 1;
+            v = reinterpret_cast<const cplx *>(jp.src[last])[(i >> jp.shift[last]) &
+                                                             ((1ull << jp.n_lanes[last]) - 1ull)];
+            /* the reference multiplies from the low-lane end: s_k * (s_{k+1} * (...)) */
+            for (int k = last - 1; k >= 0; --k) {
+                const cplx s = reinterpret_cast<const cplx *>(jp.src[k])[(i >> jp.shift[k]) &
+                                                                         ((1ull << jp.n_lanes[k]) - 1ull)];
+                v = cmul_exact(s, v);
+            }
+        } else {
+            v.x = (real)0;
+            v.y = (real)0;
+        }
+        dst[i] = v;
+    }
+}
+
+/* ---- amplitude / probability readout (CPUQubitsStatesGetter.cpp:34-157) ------------------- */
+__device__ __forceinline__ uint64_t ext_to_local(const LaneTable &t, uint64_t ext) {
+    uint64_t local = 0;
+    for (int l = 0; l < t.n_lanes; ++l) local |= ((ext >> t.ext[l]) & 1ull) << l;
+    return local;
+}
+
+template <typename real, int MATHOP>
+__global__ void __launch_bounds__(256)
+get_states_kernel(void *__restrict__ out, const __grid_constant__ GatherParams gp, uint64_t empty_mask,
+                  int64_t first, int64_t count, int64_t start, int64_t step) {
+    typedef typename Cplx<real>::type cplx;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        const uint64_t ext = (uint64_t)(start + step * (first + j));
+        const bool empty = (ext & empty_mask) != 0;
+        if (MATHOP == 0) {
+            cplx v;
+            v.x = empty ? (real)0 : (real)1;
+            v.y = (real)0;
+            if (!empty)
+                for (int q = 0; q < gp.n_qstates; ++q) {
+                    const cplx s = reinterpret_cast<const cplx *>(gp.qs[q].amp)[ext_to_local(gp.qs[q], ext)];
+                    v = cmul_exact(v, s);
+                }
+            reinterpret_cast<cplx *>(out)[j] = v;
+        } else {
+            real v = empty ? (real)0 : (real)1;
+            if (!empty)
+                for (int q = 0; q < gp.n_qstates; ++q) {
+                    const cplx s = reinterpret_cast<const cplx *>(gp.qs[q].amp)[ext_to_local(gp.qs[q], ext)];
+                    v = mul_rn(v, abs2_exact(s));
+                }
+            reinterpret_cast<real *>(out)[j] = v;
+        }
+    }
+}
+
+/* ---- marginal probabilities, hidden lanes in the LSBs (CPUQubitsStatesGetter.cpp:159-254) -- */
+template <typename real>
+__global__ void __launch_bounds__(256)
+prob_array_kernel(double *__restrict__ out, const __grid_constant__ GatherParams gp, int n_hidden,
+                  int64_t first, int64_t count) {
+    typedef typename Cplx<real>::type cplx;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t n_sum = 1ull << n_hidden;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        const uint64_t d = (uint64_t)(first + j);
+        double sum = 0.;
+        for (uint64_t h = 0; h < n_sum; ++h) {
+            const uint64_t ext = (d << n_hidden) | h;
+            real v = (real)1;
+            for (int q = 0; q < gp.n_qstates; ++q) {
+                const cplx s = reinterpret_cast<const cplx *>(gp.qs[q].amp)[ext_to_local(gp.qs[q], ext)];
+                v = mul_rn(v, abs2_exact(s));
+            }
+            sum = add_rn(sum, (double)v);
+        }
+        out[j] = sum;
+    }
+}
+
+/* out[j] = sum of 2^log2_group consecutive inputs (sequential, double) */
+__global__ void __launch_bounds__(256)
+reduce_groups_kernel(double *__restrict__ out, const double *__restrict__ in, int log2_group, int64_t count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t g = 1ll << log2_group;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        double sum = 0.;
+        for (int64_t h = 0; h < g; ++h) sum = add_rn(sum, in[j * g + h]);
+        out[j] = sum;
+    }
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+cast_from_double_kernel(real *__restrict__ out, const double *__restrict__ in, int64_t count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride)
+        out[j] = (real)in[j];
+}
+
+/* ---- sampling pool: inclusive scan (CPUSamplingPool.cpp:8-63) ------------------------------ */
+#define SCAN_THREADS 256
+#define SCAN_PER_THREAD 16
+#define SCAN_BLOCK (SCAN_THREADS * SCAN_PER_THREAD)
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_phase1_kernel(const double *__restrict__ prob, int64_t n, double *__restrict__ block_sums) {
+    const int64_t begin = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    double acc = 0.;
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u)
+        if (begin + u < n) acc += prob[begin + u];
+    /* same combination tree as phase 3 uses for the thread offsets */
+    __shared__ double tsum[SCAN_THREADS];
+    tsum[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+        for (int t = 0; t < SCAN_THREADS; ++t) s += tsum[t];
+        block_sums[blockIdx.x] = s;
+    }
+}
+
+/* exclusive scan of the block sums in place (sequential per thread chunk + sequential over
+ * chunk totals: deterministic), grand total to *total */
+__global__ void __launch_bounds__(1024)
+scan_phase2_kernel(double *__restrict__ block_sums, int64_t n_blocks, double *__restrict__ total) {
+    __shared__ double chunk_sum[1024];
+    const int64_t per = (n_blocks + blockDim.x - 1) / blockDim.x;
+    const int64_t begin = (int64_t)threadIdx.x * per;
+    const int64_t end = begin + per < n_blocks ? begin + per : n_blocks;
+    double acc = 0.;
+    for (int64_t i = begin; i < end; ++i) acc += block_sums[i];
+    chunk_sum[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+        for (int t = 0; t < (int)blockDim.x; ++t) {
+            const double c = chunk_sum[t];
+            chunk_sum[t] = s;
+            s += c;
+        }
+        *total = s;
+    }
+    __syncthreads();
+    acc = chunk_sum[threadIdx.x];
+    for (int64_t i = begin; i < end; ++i) {
+        const double c = block_sums[i];
+        block_sums[i] = acc;
+        acc += c;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_phase3_kernel(double *__restrict__ prob, int64_t n, const double *__restrict__ block_sums,
+                   const double *__restrict__ total) {
+    const int64_t begin = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    double v[SCAN_PER_THREAD];
+    double acc = 0.;
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) {
+        acc += (begin + u < n) ? prob[begin + u] : 0.;
+        v[u] = acc;
+    }
+    __shared__ double tsum[SCAN_THREADS];
+    tsum[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+        for (int t = 0; t < SCAN_THREADS; ++t) {
+            const double c = tsum[t];
+            tsum[t] = s;
+            s += c;
+        }
+    }
+    __syncthreads();
+    const double offset = block_sums[blockIdx.x] + tsum[threadIdx.x];
+    const double norm = 1. / *total; /* CPUSamplingPool.cpp:36: norm = 1 / sum, then cum *= norm */
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u)
+        if (begin + u < n) prob[begin + u] = (offset + v[u]) * norm;
+}
+
+/* ---- sampling pool: upper_bound search + empty-lane deposit (CPUSamplingPool.cpp:71-81) ---- */
+__global__ void __launch_bounds__(256)
+sample_kernel(const double *__restrict__ cum, int64_t n_states, const double *__restrict__ rnd,
+              int64_t *__restrict__ obs, int n_samples, SortedBits empty, int fp32) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    double r = rnd[i];
+    if (fp32) r = (double)(float)r;
+    int64_t lo = 0, hi = n_states;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cum[mid] > r)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    if (lo > n_states - 1) lo = n_states - 1;
+    uint64_t v = (uint64_t)lo;
+    for (int k = 0; k < empty.n; ++k) v = insert_zero(v, empty.pos[k]);
+    obs[i] = (int64_t)v;
+}
+
+inline unsigned grid_for(uint64_t n, unsigned nthr, unsigned cap) {
+    uint64_t b = (n + nthr - 1) / nthr;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (unsigned)b;
+}
+
+/* grid-stride kernels: enough CTAs to fill 148 SMs several times over */
+const unsigned kStreamCap = 148 * 16;
+
+} // namespace
+
+cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,
+                                   cudaStream_t stream) {
+    const size_t bytes = n_amps * (prec == 1 ? 16 : 8);
+    cudaError_t rc = cudaMemsetAsync(amp, 0, bytes, stream);
+    if (rc != cudaSuccess) return rc;
+    if (prec == 1)
+        set_one_kernel<double><<<1, 1, 0, stream>>>(reinterpret_cast<double2 *>(amp), one_at);
+    else
+        set_one_kernel<float><<<1, 1, 0, stream>>>(reinterpret_cast<float2 *>(amp), one_at);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prob0(int prec, const void *amp, int n_lanes, int lane, double *d_partials,
+                         double *d_result, cudaStream_t stream) {
+    const uint64_t n_half = 1ull << (n_lanes - 1);
+    const unsigned nblocks = grid_for((n_half + 3) / 4, 256, 148 * 8);
+    if (prec == 1)
+        prob0_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<const double2 *>(amp), n_half,
+                                                         lane, d_partials);
+    else
+        prob0_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<const float2 *>(amp), n_half,
+                                                        lane, d_partials);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    final_sum_kernel<<<1, 1024, 0, stream>>>(d_partials, (int)nblocks, d_result);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decohere(int prec, void *amp, int n_lanes, int lane, int value, double norm,
+                            cudaStream_t stream) {
+    const uint64_t n = 1ull << n_lanes;
+    const unsigned nblocks = grid_for(n, 256, kStreamCap);
+    if (prec == 1)
+        decohere_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double2 *>(amp), n, lane,
+                                                            value, norm);
+    else
+        decohere_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float2 *>(amp), n, lane,
+                                                           value, (float)norm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decohere_separate(int prec, void *dst, const void *src, int n_src_lanes, int lane,
+                                     int value, double norm, cudaStream_t stream) {
+    const uint64_t n_dst = 1ull << (n_src_lanes - 1);
+    const unsigned nblocks = grid_for(n_dst, 256, kStreamCap);
+    if (prec == 1)
+        decohere_separate_kernel<double><<<nblocks, 256, 0, stream>>>(
+            reinterpret_cast<double2 *>(dst), reinterpret_cast<const double2 *>(src), n_dst, lane, value,
+            norm);
+    else
+        decohere_separate_kernel<float><<<nblocks, 256, 0, stream>>>(
+            reinterpret_cast<float2 *>(dst), reinterpret_cast<const float2 *>(src), n_dst, lane, value,
+            (float)norm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_reset(int prec, void *amp, int n_lanes, int lane, cudaStream_t stream) {
+    const uint64_t n_half = 1ull << (n_lanes - 1);
+    const unsigned nblocks = grid_for(n_half, 256, kStreamCap);
+    if (prec == 1)
+        apply_reset_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double2 *>(amp), n_half,
+                                                               lane);
+    else
+        apply_reset_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float2 *>(amp), n_half,
+                                                              lane);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_join(int prec, void *dst, int n_dst_lanes, int n_product_lanes, const JoinParams &jp,
+                        cudaStream_t stream) {
+    const uint64_t n_dst = 1ull << n_dst_lanes, n_product = 1ull << n_product_lanes;
+    const unsigned nblocks = grid_for(n_dst, 256, kStreamCap);
+    if (prec == 1)
+        join_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double2 *>(dst), n_dst,
+                                                        n_product, jp);
+    else
+        join_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float2 *>(dst), n_dst, n_product,
+                                                       jp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_get_states(int prec, void *d_out, int mathop, const GatherParams &gp,
+                              uint64_t empty_mask, int64_t first, int64_t count, int64_t start,
+                              int64_t step, cudaStream_t stream) {
+    const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
+    if (prec == 1) {
+        if (mathop == 0)
+            get_states_kernel<double, 0><<<nblocks, 256, 0, stream>>>(d_out, gp, empty_mask, first, count,
+                                                                     start, step);
+        else
+            get_states_kernel<double, 1><<<nblocks, 256, 0, stream>>>(d_out, gp, empty_mask, first, count,
+                                                                     start, step);
+    } else {
+        if (mathop == 0)
+            get_states_kernel<float, 0><<<nblocks, 256, 0, stream>>>(d_out, gp, empty_mask, first, count,
+                                                                    start, step);
+        else
+            get_states_kernel<float, 1><<<nblocks, 256, 0, stream>>>(d_out, gp, empty_mask, first, count,
+                                                                    start, step);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prob_array(int prec, double *d_out, const GatherParams &gp, int n_hidden, int64_t first,
+                              int64_t count, cudaStream_t stream) {
+    const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
+    if (prec == 1)
+        prob_array_kernel<double><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
+    else
+        prob_array_kernel<float><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_groups(double *d_out, const double *d_in, int log2_group, int64_t count,
+                                 cudaStream_t stream) {
+    const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
+    reduce_groups_kernel<<<nblocks, 256, 0, stream>>>(d_out, d_in, log2_group, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, int64_t count,
+                                    cudaStream_t stream) {
+    const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
+    if (prec == 1)
+        cast_from_double_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double *>(d_out), d_in,
+                                                                    count);
+    else
+        cast_from_double_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float *>(d_out), d_in,
+                                                                   count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_phase1(const double *d_prob, int64_t n, double *d_block_sums, cudaStream_t stream) {
+    const unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    scan_phase1_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d_total, cudaStream_t stream) {
+    scan_phase2_kernel<<<1, 1024, 0, stream>>>(d_block_sums, n_blocks, d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums, const double *d_total,
+                               cudaStream_t stream) {
+    const unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    scan_phase3_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums, d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample(int prec, const double *d_cum, int n_lanes, const double *d_rand, int64_t *d_obs,
+                          int n_samples, SortedBits empty_lanes, cudaStream_t stream) {
+    if (n_samples <= 0) return cudaSuccess;
+    const unsigned nblocks = (unsigned)((n_samples + 255) / 256);
+    sample_kernel<<<nblocks, 256, 0, stream>>>(d_cum, 1ll << n_lanes, d_rand, d_obs, n_samples, empty_lanes,
+                                               prec == 2 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+} // namespace qgb

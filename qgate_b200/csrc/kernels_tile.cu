@@ -1,0 +1,364 @@
+/*
+ * kernels_tile.cu — gate application kernels (sm_100a).
+ *
+ *   tile_pass_kernel   the fused pass: one CTA stages a 2^T-amplitude tile in shared
+ *                      memory, applies every gate of the pass, writes the tile back.
+ *                      One read + one write of the state vector per PASS, not per gate.
+ *   simple_gate_kernel one (multi-)controlled 2x2 per launch, one amplitude pair per
+ *                      thread; used for state vectors too small for a tile.
+ *
+ * Arithmetic being reproduced: qgate/simulator/src/CPUQubitProcessor.cpp:307-362
+ * (o0 = m00 q0 + m01 q1, o1 = m10 q0 + m11 q1 on every pair whose control bits are 1),
+ * matrix cast to the state precision first (CPUQubitProcessor.cpp:312).  The incumbent
+ * device code this replaces is DeviceProcPrimitives.cu:198-249 (one pair per thread, one
+ * launch per gate, 12 KB of lookup tables per controlled gate).
+ *
+ * Shared-memory layout: tile element e lives at byte address (e * sizeof(complex)) with
+ * bits [6:4] XORed by bits [9:7] — the 128-byte swizzle TMA tensor maps produce — so that
+ * any choice of register bits leaves the threads of a quarter/half warp on distinct banks
+ * (the planner orders the thread bits accordingly, planner.cpp: choose_thread_bits).
+ */
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace qgb {
+
+namespace {
+
+template <typename real> struct Cplx;
+template <> struct Cplx<float> { typedef float2 type; };
+template <> struct Cplx<double> { typedef double2 type; };
+
+template <typename real> __device__ __forceinline__ uint32_t swz(uint32_t e);
+template <> __device__ __forceinline__ uint32_t swz<double>(uint32_t e) { return e ^ ((e >> 3) & 7u); }
+template <> __device__ __forceinline__ uint32_t swz<float>(uint32_t e) { return e ^ (((e >> 4) & 7u) << 1); }
+
+template <int K> __device__ __forceinline__ uint32_t reg_offset(int r, const uint32_t (&rb)[K]) {
+    uint32_t off = 0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (r & (1 << j)) off |= rb[j];
+    return off;
+}
+
+/* ---- per-op bodies; `a` is the thread's register file of 2^K amplitudes ---------------- */
+
+template <typename real, int K, int J>
+__device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                          uint32_t cm, uint32_t ebase, const uint32_t (&rb)[K]) {
+    const real m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3];
+    const real m10r = m[4], m10i = m[5], m11r = m[6], m11i = m[7];
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        const int r1 = r0 | (1 << J);
+        const uint32_t e0 = ebase | reg_offset<K>(r0, rb);
+        if ((e0 & cm) == cm) {
+            const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
+            a[r0].x = m00r * q0r - m00i * q0i + m01r * q1r - m01i * q1i;
+            a[r0].y = m00r * q0i + m00i * q0r + m01r * q1i + m01i * q1r;
+            a[r1].x = m10r * q0r - m10i * q0i + m11r * q1r - m11i * q1i;
+            a[r1].y = m10r * q0i + m10i * q0r + m11r * q1i + m11i * q1r;
+        }
+    }
+}
+
+template <typename real, int K, int J>
+__device__ __forceinline__ void apply_xswap(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                            bool pure_swap, uint32_t cm, uint32_t ebase,
+                                            const uint32_t (&rb)[K]) {
+    const real m01r = m[0], m01i = m[1], m10r = m[2], m10i = m[3];
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        const int r1 = r0 | (1 << J);
+        const uint32_t e0 = ebase | reg_offset<K>(r0, rb);
+        if ((e0 & cm) == cm) {
+            const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
+            if (pure_swap) {
+                a[r0].x = q1r; a[r0].y = q1i;
+                a[r1].x = q0r; a[r1].y = q0i;
+            } else {
+                a[r0].x = m01r * q1r - m01i * q1i;
+                a[r0].y = m01r * q1i + m01i * q1r;
+                a[r1].x = m10r * q0r - m10i * q0i;
+                a[r1].y = m10r * q0i + m10i * q0r;
+            }
+        }
+    }
+}
+
+template <typename real, int K>
+__device__ __forceinline__ void apply_phase(typename Cplx<real>::type (&a)[1 << K], real dr, real di,
+                                            uint32_t cm, uint32_t ebase, const uint32_t (&rb)[K]) {
+#pragma unroll
+    for (int r = 0; r < (1 << K); ++r) {
+        const uint32_t e = ebase | reg_offset<K>(r, rb);
+        if ((e & cm) == cm) {
+            const real qr = a[r].x, qi = a[r].y;
+            a[r].x = dr * qr - di * qi;
+            a[r].y = dr * qi + di * qr;
+        }
+    }
+}
+
+template <typename real, int K>
+__device__ __forceinline__ void apply_diag(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                           uint32_t tbit, uint32_t cm, uint32_t ebase,
+                                           const uint32_t (&rb)[K]) {
+    const real d0r = m[0], d0i = m[1], d1r = m[2], d1i = m[3];
+#pragma unroll
+    for (int r = 0; r < (1 << K); ++r) {
+        const uint32_t e = ebase | reg_offset<K>(r, rb);
+        if ((e & cm) == cm) {
+            const bool one = (e >> tbit) & 1u;
+            const real dr = one ? d1r : d0r, di = one ? d1i : d0i;
+            const real qr = a[r].x, qi = a[r].y;
+            a[r].x = dr * qr - di * qi;
+            a[r].y = dr * qi + di * qr;
+        }
+    }
+}
+
+template <typename real, int K>
+__device__ __forceinline__ void apply_op(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
+                                         uint64_t base, uint32_t ebase, const uint32_t (&rb)[K]) {
+    /* controls outside the tile are the same for the whole CTA */
+    if ((base & op.ctrl_out) != op.ctrl_out) return;
+    const uint32_t cm = op.ctrl_tile;
+    switch (op.kind) {
+    case OP_GEN:
+        switch (op.bit) {
+        case 0: apply_gen<real, K, 0>(a, op.m, cm, ebase, rb); break;
+        case 1: if (K > 1) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, op.m, cm, ebase, rb); break;
+        case 2: if (K > 2) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, op.m, cm, ebase, rb); break;
+        case 3: if (K > 3) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, op.m, cm, ebase, rb); break;
+        }
+        break;
+    case OP_XSWAP: {
+        const bool pure = op.pad_ != 0;
+        switch (op.bit) {
+        case 0: apply_xswap<real, K, 0>(a, op.m, pure, cm, ebase, rb); break;
+        case 1: if (K > 1) apply_xswap<real, K, (K > 1 ? 1 : 0)>(a, op.m, pure, cm, ebase, rb); break;
+        case 2: if (K > 2) apply_xswap<real, K, (K > 2 ? 2 : 0)>(a, op.m, pure, cm, ebase, rb); break;
+        case 3: if (K > 3) apply_xswap<real, K, (K > 3 ? 3 : 0)>(a, op.m, pure, cm, ebase, rb); break;
+        }
+        break;
+    }
+    case OP_PHASE:
+        apply_phase<real, K>(a, op.m[0], op.m[1], cm, ebase, rb);
+        break;
+    case OP_DIAG:
+        apply_diag<real, K>(a, op.m, (uint32_t)op.bit, cm, ebase, rb);
+        break;
+    case OP_DIAG_OUT: {
+        const bool one = (base >> op.bit) & 1ull;
+        apply_phase<real, K>(a, one ? op.m[2] : op.m[0], one ? op.m[3] : op.m[1], cm, ebase, rb);
+        break;
+    }
+    }
+}
+
+/* ---- the fused pass ------------------------------------------------------------------ */
+
+template <typename real, int K, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
+                 typename Cplx<real>::type *__restrict__ amp) {
+    typedef typename Cplx<real>::type cplx;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int T = prog.T, L = prog.L;
+    cplx *tile = reinterpret_cast<cplx *>(smem_raw);
+    uint64_t *choff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(cplx) << T));
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
+
+    /* index of this CTA's tile origin: blockIdx bits deposited on the non-tile lanes */
+    uint64_t base = 0;
+    {
+        const uint64_t bid = blockIdx.x;
+        const int nrest = prog.n_lanes - T;
+        for (int i = 0; i < nrest; ++i) base |= ((bid >> i) & 1ull) << prog.rest_lane[i];
+    }
+    /* global offset of each run of 2^L contiguous amplitudes of the tile */
+    {
+        const uint32_t nchunks = 1u << (T - L);
+        for (uint32_t c = tid; c < nchunks; c += nthr) {
+            uint64_t off = 0;
+            for (int b = 0; b < T - L; ++b) off |= (uint64_t)((c >> b) & 1u) << prog.tile_lane[L + b];
+            choff[c] = off;
+        }
+    }
+    __syncthreads();
+    const uint32_t lowmask = (1u << L) - 1u;
+
+    /* global -> shared, 16 bytes per thread per request, coalesced along the low lanes */
+    if (sizeof(real) == 8) {
+#pragma unroll
+        for (int i = 0; i < (1 << K); ++i) {
+            const uint32_t e = tid + i * nthr;
+            const uint64_t g = base | choff[e >> L] | (e & lowmask);
+            tile[swz<real>(e)] = __ldcs(&amp[g]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (1 << K) / 2; ++i) {
+            const uint32_t e = 2u * (tid + i * nthr);
+            const uint64_t g = base | choff[e >> L] | (e & lowmask);
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(&amp[g]));
+            *reinterpret_cast<float4 *>(&tile[swz<real>(e)]) = v;
+        }
+    }
+    __syncthreads();
+
+    for (int s = 0; s < prog.n_stages; ++s) {
+        const Stage &st = prog.stage[s];
+        if (st.op_begin == st.op_end) continue;
+        uint32_t ebase = 0;
+        for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
+        uint32_t rb[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) rb[j] = 1u << st.R[j];
+
+        cplx a[1 << K];
+#pragma unroll
+        for (int r = 0; r < (1 << K); ++r) a[r] = tile[swz<real>(ebase | reg_offset<K>(r, rb))];
+
+        for (int o = st.op_begin; o < st.op_end; ++o) apply_op<real, K>(a, prog.op[o], base, ebase, rb);
+
+#pragma unroll
+        for (int r = 0; r < (1 << K); ++r) tile[swz<real>(ebase | reg_offset<K>(r, rb))] = a[r];
+        __syncthreads();
+    }
+
+    /* shared -> global */
+    if (sizeof(real) == 8) {
+#pragma unroll
+        for (int i = 0; i < (1 << K); ++i) {
+            const uint32_t e = tid + i * nthr;
+            const uint64_t g = base | choff[e >> L] | (e & lowmask);
+            __stcs(&amp[g], tile[swz<real>(e)]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < (1 << K) / 2; ++i) {
+            const uint32_t e = 2u * (tid + i * nthr);
+            const uint64_t g = base | choff[e >> L] | (e & lowmask);
+            __stcs(reinterpret_cast<float4 *>(&amp[g]), *reinterpret_cast<const float4 *>(&tile[swz<real>(e)]));
+        }
+    }
+}
+
+/* ---- one gate per launch (small state vectors) ------------------------------------------ */
+
+template <typename real>
+struct Mat2 {
+    real m[8];
+};
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs, SortedBits skip,
+                   uint64_t target_bit, uint64_t ctrl_mask, Mat2<real> mat) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_pairs) return;
+    /* insert a 0 at every skipped position (target and controls), ascending */
+    uint64_t idx = gid;
+    for (int i = 0; i < skip.n; ++i) {
+        const uint64_t lo = idx & ((1ull << skip.pos[i]) - 1ull);
+        idx = ((idx - lo) << 1) | lo;
+    }
+    const uint64_t i0 = idx | ctrl_mask, i1 = i0 | target_bit;
+    const typename Cplx<real>::type q0 = amp[i0], q1 = amp[i1];
+    const real *m = mat.m;
+    typename Cplx<real>::type o0, o1;
+    o0.x = m[0] * q0.x - m[1] * q0.y + m[2] * q1.x - m[3] * q1.y;
+    o0.y = m[0] * q0.y + m[1] * q0.x + m[2] * q1.y + m[3] * q1.x;
+    o1.x = m[4] * q0.x - m[5] * q0.y + m[6] * q1.x - m[7] * q1.y;
+    o1.y = m[4] * q0.y + m[5] * q0.x + m[6] * q1.y + m[7] * q1.x;
+    amp[i0] = o0;
+    amp[i1] = o1;
+}
+
+template <typename real, int K, int NT, int MINB>
+cudaError_t launch_variant(const PassProgram<real> &prog, void *amp, size_t smem, cudaStream_t stream) {
+    const unsigned nthr = 1u << (prog.T - K);
+    const unsigned nblocks = 1u << (prog.n_lanes - prog.T);
+    tile_pass_kernel<real, K, NT, MINB><<<nblocks, nthr, smem, stream>>>(
+        prog, reinterpret_cast<typename Cplx<real>::type *>(amp));
+    return cudaGetLastError();
+}
+
+template <typename real, int K, int NT, int MINB>
+cudaError_t configure_variant(int max_smem_optin) {
+    return cudaFuncSetAttribute(tile_pass_kernel<real, K, NT, MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+}
+
+} // namespace
+
+size_t tile_pass_smem_bytes(int prec, int T, int L) {
+    const size_t elem = prec == 1 ? 16 : 8;
+    return (elem << T) + (sizeof(uint64_t) << (T - L));
+}
+
+#define QGB_K64 3
+#define QGB_K32 4
+
+cudaError_t tile_pass_configure(int max_smem_optin) {
+    cudaError_t rc;
+    if ((rc = configure_variant<double, QGB_K64, 256, 3>(max_smem_optin)) != cudaSuccess) return rc;
+    if ((rc = configure_variant<double, QGB_K64, 512, 2>(max_smem_optin)) != cudaSuccess) return rc;
+    if ((rc = configure_variant<double, QGB_K64, 1024, 1>(max_smem_optin)) != cudaSuccess) return rc;
+    if ((rc = configure_variant<float, QGB_K32, 256, 3>(max_smem_optin)) != cudaSuccess) return rc;
+    if ((rc = configure_variant<float, QGB_K32, 512, 2>(max_smem_optin)) != cudaSuccess) return rc;
+    if ((rc = configure_variant<float, QGB_K32, 1024, 1>(max_smem_optin)) != cudaSuccess) return rc;
+    return cudaSuccess;
+}
+
+template <>
+cudaError_t launch_tile_pass<double>(const PassProgram<double> &prog, void *amp, cudaStream_t stream) {
+    if (prog.K != QGB_K64 || prog.T < prog.K || prog.T - prog.K > 10) return cudaErrorInvalidValue;
+    const size_t smem = tile_pass_smem_bytes(1, prog.T, prog.L);
+    const int nthr = 1 << (prog.T - prog.K);
+    if (nthr <= 256) return launch_variant<double, QGB_K64, 256, 3>(prog, amp, smem, stream);
+    if (nthr <= 512) return launch_variant<double, QGB_K64, 512, 2>(prog, amp, smem, stream);
+    return launch_variant<double, QGB_K64, 1024, 1>(prog, amp, smem, stream);
+}
+
+template <>
+cudaError_t launch_tile_pass<float>(const PassProgram<float> &prog, void *amp, cudaStream_t stream) {
+    if (prog.K != QGB_K32 || prog.T < prog.K || prog.T - prog.K > 10 || prog.L < 1)
+        return cudaErrorInvalidValue;
+    const size_t smem = tile_pass_smem_bytes(2, prog.T, prog.L);
+    const int nthr = 1 << (prog.T - prog.K);
+    if (nthr <= 256) return launch_variant<float, QGB_K32, 256, 3>(prog, amp, smem, stream);
+    if (nthr <= 512) return launch_variant<float, QGB_K32, 512, 2>(prog, amp, smem, stream);
+    return launch_variant<float, QGB_K32, 1024, 1>(prog, amp, smem, stream);
+}
+
+cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
+                               uint64_t ctrl_mask, cudaStream_t stream) {
+    SortedBits skip;
+    skip.n = 0;
+    const uint64_t touched = ctrl_mask | (1ull << target);
+    for (int lane = 0; lane < n_lanes; ++lane)
+        if (touched & (1ull << lane)) skip.pos[skip.n++] = (int8_t)lane;
+    const uint64_t n_pairs = 1ull << (n_lanes - skip.n);
+    const unsigned nthr = 256;
+    const unsigned nblocks = (unsigned)((n_pairs + nthr - 1) / nthr);
+    if (prec == 1) {
+        Mat2<double> m;
+        for (int i = 0; i < 8; ++i) m.m[i] = mat8[i];
+        simple_gate_kernel<double><<<nblocks, nthr, 0, stream>>>(
+            reinterpret_cast<double2 *>(amp), n_pairs, skip, 1ull << target, ctrl_mask, m);
+    } else {
+        Mat2<float> m;
+        for (int i = 0; i < 8; ++i) m.m[i] = (float)mat8[i];
+        simple_gate_kernel<float><<<nblocks, nthr, 0, stream>>>(
+            reinterpret_cast<float2 *>(amp), n_pairs, skip, 1ull << target, ctrl_mask, m);
+    }
+    return cudaGetLastError();
+}
+
+} // namespace qgb

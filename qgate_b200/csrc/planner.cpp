@@ -1,0 +1,303 @@
+/*
+ * planner.cpp — deferred gate queue -> pass programs (see program.h for the vocabulary).
+ *
+ * The reference executes one kernel per gate (CUDAQubitProcessor.cpp:270-335); it has no
+ * counterpart of this file.  What must be preserved is the RESULT of applying the queued
+ * gates in submission order (CPUQubitProcessor.cpp:307-362), so the planner only reorders
+ * gates that commute: two gates commute when, on every lane they share, both act
+ * diagonally (a control acts as the projector |1><1|, a diagonal matrix acts diagonally).
+ */
+#include "planner.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace qgb {
+
+namespace {
+
+inline void cmul(const double *a, const double *b, double *out) {
+    /* out = a * b, complex */
+    double re = a[0] * b[0] - a[1] * b[1];
+    double im = a[0] * b[1] + a[1] * b[0];
+    out[0] = re;
+    out[1] = im;
+}
+
+/* m = a * b for 2x2 complex matrices stored (re,im) row-major */
+void matmul2(const double *a, const double *b, double *m) {
+    double t[8];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 2; ++c) {
+            double p0[2], p1[2];
+            cmul(&a[(r * 2 + 0) * 2], &b[(0 * 2 + c) * 2], p0);
+            cmul(&a[(r * 2 + 1) * 2], &b[(1 * 2 + c) * 2], p1);
+            t[(r * 2 + c) * 2] = p0[0] + p1[0];
+            t[(r * 2 + c) * 2 + 1] = p0[1] + p1[1];
+        }
+    std::memcpy(m, t, sizeof(t));
+}
+
+inline int popcount64(uint64_t v) { return __builtin_popcountll(v); }
+
+/* shared-memory bank class of a tile bit under the 128-byte XOR swizzle the kernels use
+ * (byte address bits [6:4] ^= bits [9:7]); -1: the bit does not move the bank. */
+inline int bank_class(int tile_bit, bool fp32) {
+    if (fp32) { /* 8-byte elements, 16 lanes of a half warp must hit 16 distinct 8-byte slots */
+        if (tile_bit == 0) return 0;
+        if (tile_bit < 7) return 1 + (tile_bit - 1) % 3;
+        return -1;
+    }
+    /* 16-byte elements, 8 lanes of a quarter warp must hit 8 distinct 16-byte slots */
+    if (tile_bit < 6) return tile_bit % 3;
+    return -1;
+}
+
+void choose_thread_bits(const int8_t *R, int K, int T, bool fp32, int8_t *W) {
+    bool used[QGB_MAX_TILE_LANES] = {false};
+    for (int j = 0; j < K; ++j) used[R[j]] = true;
+    int n_classes = fp32 ? 4 : 3;
+    int n = 0;
+    for (int c = 0; c < n_classes; ++c)
+        for (int b = 0; b < T; ++b)
+            if (!used[b] && bank_class(b, fp32) == c) {
+                W[n++] = (int8_t)b;
+                used[b] = true;
+                break;
+            }
+    for (int b = 0; b < T; ++b)
+        if (!used[b]) W[n++] = (int8_t)b;
+    for (; n < QGB_MAX_TILE_LANES; ++n) W[n] = 0;
+}
+
+struct Picked {
+    int queue_idx;
+    int stage;
+};
+
+} // namespace
+
+bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
+    if (merge && !queue.empty()) {
+        if (g.ctrl_mask == 0) {
+            uint64_t tm = 1ull << g.target;
+            int lo = std::max(0, (int)queue.size() - 256);
+            for (int i = (int)queue.size() - 1; i >= lo; --i) {
+                Gate &p = queue[i];
+                uint64_t touched = p.ctrl_mask | (1ull << p.target);
+                if (!(touched & tm)) continue;
+                if (p.ctrl_mask == 0 && p.target == g.target) {
+                    matmul2(g.m, p.m, p.m);
+                    return true;
+                }
+                break;
+            }
+        } else {
+            Gate &p = queue.back();
+            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask) {
+                matmul2(g.m, p.m, p.m);
+                return true;
+            }
+        }
+    }
+    queue.push_back(g);
+    return false;
+}
+
+template <typename real>
+void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
+               PassProgram<real> &prog, PlanStats &stats) {
+    const int n = n_lanes;
+    const int T = std::min(std::min(cfg.T, n), QGB_MAX_TILE_LANES);
+    /* at least one free tile lane, or a non-diagonal gate on a high lane could never run */
+    const int L = T < n ? std::min(cfg.L, T - 1) : std::min(cfg.L, T);
+    const int K = std::min(std::min(cfg.K, T), QGB_MAX_REG_BITS);
+    const int max_ops = std::min(cfg.max_ops, QGB_MAX_OPS);
+    const int max_stages = std::min(cfg.max_stages, QGB_MAX_STAGES);
+    const uint64_t all_lanes = n >= 64 ? ~0ull : ((1ull << n) - 1);
+
+    uint64_t S = (T >= n) ? all_lanes : ((1ull << L) - 1);
+    int count = popcount64(S);
+    uint64_t blockedX = 0, blockedZ = 0;
+    std::vector<Picked> picked;
+    std::vector<uint64_t> stageR; /* lane masks of the register bits of each stage */
+    int first_block = -1;
+    int cost = 0;
+
+    for (int i = 0; i < (int)queue.size(); ++i) {
+        if (first_block >= 0 && i - first_block > cfg.lookahead) break;
+        const Gate &g = queue[i];
+        const bool diag = gate_is_diag(g);
+        const uint64_t tm = 1ull << g.target;
+        const uint64_t xq = diag ? 0 : tm;
+        const uint64_t zq = g.ctrl_mask | (diag ? tm : 0);
+        bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
+        const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : 4);
+        if (!blocked && ((int)picked.size() >= max_ops || (cost + gcost > cfg.max_cost && !picked.empty())))
+            blocked = true;
+        bool add_lane = false;
+        if (!blocked && xq && !(S & xq)) {
+            if (count < T)
+                add_lane = true;
+            else
+                blocked = true;
+        }
+        /* stage bookkeeping: 0 = stay in the open stage, 1 = open a new stage, 2 = add the
+         * target to the open stage's register bits */
+        int action = 0;
+        if (!blocked) {
+            if (stageR.empty())
+                action = 1;
+            else if (xq && !(stageR.back() & xq))
+                action = popcount64(stageR.back()) < K ? 2 : 1;
+            if (action == 1 && (int)stageR.size() >= max_stages) blocked = true;
+        }
+        if (blocked) {
+            blockedX |= xq;
+            blockedZ |= zq;
+            if (first_block < 0) first_block = i;
+            if ((blockedX & all_lanes) == all_lanes) break;
+            continue;
+        }
+        if (add_lane) {
+            S |= xq;
+            ++count;
+        }
+        if (action == 1)
+            stageR.push_back(xq);
+        else if (action == 2)
+            stageR.back() |= xq;
+        picked.push_back({i, (int)stageR.size() - 1});
+        cost += gcost;
+    }
+
+    /* fill the tile with the highest unused lanes when fewer than T were needed (keeps the
+     * kernel shape fixed; any lane works because unused tile lanes are just carried). */
+    for (int lane = n - 1; lane >= 0 && count < T; --lane)
+        if (!(S & (1ull << lane))) {
+            S |= 1ull << lane;
+            ++count;
+        }
+
+    std::memset(&prog, 0, sizeof(prog));
+    prog.n_lanes = n;
+    prog.T = T;
+    prog.L = L;
+    prog.K = K;
+    int lane_to_tile[64];
+    {
+        int p = 0, r = 0;
+        for (int lane = 0; lane < n; ++lane) {
+            if (S & (1ull << lane)) {
+                lane_to_tile[lane] = p;
+                prog.tile_lane[p++] = (int8_t)lane;
+            } else {
+                lane_to_tile[lane] = -1;
+                prog.rest_lane[r++] = (int8_t)lane;
+            }
+        }
+    }
+    /* stages */
+    const int n_stages = std::max<int>(1, (int)stageR.size());
+    prog.n_stages = n_stages;
+    for (int s = 0; s < n_stages; ++s) {
+        Stage &st = prog.stage[s];
+        uint64_t Rl = s < (int)stageR.size() ? stageR[s] : 0;
+        bool used[QGB_MAX_TILE_LANES] = {false};
+        int k = 0;
+        for (int lane = 0; lane < n; ++lane)
+            if (Rl & (1ull << lane)) used[lane_to_tile[lane]] = true, ++k;
+        /* pad with the highest free tile bits: keeps the low (bank-selecting) bits for threads */
+        for (int b = T - 1; b >= 0 && k < K; --b)
+            if (!used[b]) used[b] = true, ++k;
+        int j = 0;
+        for (int b = 0; b < T; ++b)
+            if (used[b]) st.R[j++] = (int8_t)b;
+        choose_thread_bits(st.R, K, T, cfg.fp32, st.W);
+        st.op_begin = st.op_end = 0;
+    }
+
+    /* ops, grouped by stage in pick order (pick order is stage-monotone) */
+    int n_ops = 0;
+    int cur_stage = -1;
+    for (const Picked &pk : picked) {
+        const Gate &g = queue[pk.queue_idx];
+        while (cur_stage < pk.stage) {
+            if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;
+            ++cur_stage;
+            prog.stage[cur_stage].op_begin = (int16_t)n_ops;
+        }
+        Op<real> &op = prog.op[n_ops++];
+        const uint64_t ctrl_in = g.ctrl_mask & S;
+        op.ctrl_out = g.ctrl_mask & ~S;
+        op.ctrl_tile = 0;
+        for (int lane = 0; lane < n; ++lane)
+            if (ctrl_in & (1ull << lane)) op.ctrl_tile |= 1u << lane_to_tile[lane];
+        const bool in_tile = (S >> g.target) & 1ull;
+        const Stage &st = prog.stage[pk.stage];
+        auto regbit = [&](int lane) {
+            int tb = lane_to_tile[lane];
+            for (int j = 0; j < K; ++j)
+                if (st.R[j] == tb) return j;
+            return -1;
+        };
+        if (gate_is_diag(g)) {
+            const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
+            if (d0_is_one) {
+                op.kind = OP_PHASE;
+                if (in_tile)
+                    op.ctrl_tile |= 1u << lane_to_tile[g.target];
+                else
+                    op.ctrl_out |= 1ull << g.target;
+                op.m[0] = (real)g.m[6];
+                op.m[1] = (real)g.m[7];
+            } else {
+                op.kind = in_tile ? OP_DIAG : OP_DIAG_OUT;
+                op.bit = in_tile ? lane_to_tile[g.target] : g.target;
+                op.m[0] = (real)g.m[0];
+                op.m[1] = (real)g.m[1];
+                op.m[2] = (real)g.m[6];
+                op.m[3] = (real)g.m[7];
+            }
+        } else if (gate_is_antidiag(g)) {
+            op.kind = OP_XSWAP;
+            op.bit = regbit(g.target);
+            op.m[0] = (real)g.m[2];
+            op.m[1] = (real)g.m[3];
+            op.m[2] = (real)g.m[4];
+            op.m[3] = (real)g.m[5];
+            op.pad_ = (g.m[2] == 1. && g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.) ? 1u : 0u;
+        } else {
+            op.kind = OP_GEN;
+            op.bit = regbit(g.target);
+            for (int e = 0; e < 8; ++e) op.m[e] = (real)g.m[e];
+        }
+    }
+    if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;
+    for (int s = cur_stage + 1; s < n_stages; ++s)
+        prog.stage[s].op_begin = prog.stage[s].op_end = (int16_t)n_ops;
+    prog.n_ops = n_ops;
+
+    /* drop the executed gates, keep the rest in order */
+    {
+        std::vector<char> done(queue.size(), 0);
+        for (const Picked &pk : picked) done[pk.queue_idx] = 1;
+        size_t w = 0;
+        for (size_t i = 0; i < queue.size(); ++i)
+            if (!done[i]) {
+                if (w != i) queue[w] = queue[i];
+                ++w;
+            }
+        queue.resize(w);
+    }
+    stats.gates_in_pass = (int)picked.size();
+    stats.ops_in_pass = n_ops;
+    stats.stages_in_pass = n_stages;
+}
+
+template void plan_pass<float>(std::vector<Gate> &, int, const PlanConfig &, PassProgram<float> &,
+                               PlanStats &);
+template void plan_pass<double>(std::vector<Gate> &, int, const PlanConfig &, PassProgram<double> &,
+                                PlanStats &);
+
+} // namespace qgb

@@ -1,0 +1,42 @@
+/*
+ * planner.h — host-side flush planner: deferred gate queue -> pass programs.
+ * Pure C++ (no CUDA); tests/native/planner_emul.cpp compiles it on the CPU box.
+ */
+#pragma once
+#include <vector>
+
+#include "program.h"
+
+namespace qgb {
+
+struct PlanConfig {
+    int T = 11;          /* tile lanes (clamped to n_lanes)                               */
+    int L = 5;           /* low contiguous lanes forced into every tile                   */
+    int K = 3;           /* register bits per stage                                       */
+    int max_ops = QGB_MAX_OPS;
+    int max_stages = QGB_MAX_STAGES;
+    int lookahead = 4096; /* how far past the first blocked gate the planner searches      */
+    bool fp32 = false;    /* selects the shared-memory bank classes used to order W[]      */
+    int max_cost = 1 << 30; /* cap on the summed op cost of a pass (see op_cost)            */
+};
+
+struct PlanStats {
+    int gates_in_pass = 0;
+    int ops_in_pass = 0;
+    int stages_in_pass = 0;
+};
+
+/* merge `g` into the queue: an uncontrolled gate folds into the previous gate on the same
+ * lane when nothing in between touches that lane; a controlled gate folds into an
+ * identical-signature gate directly before it.  Returns true when merged (queue size
+ * unchanged). */
+bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge);
+
+/* Plan ONE pass from the front of `queue` for a state vector of n_lanes lanes.  Executed
+ * gates are removed from `queue` (order of the remaining gates is preserved).  Always
+ * consumes at least one gate when the queue is not empty. */
+template <typename real>
+void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
+               PassProgram<real> &prog, PlanStats &stats);
+
+} // namespace qgb

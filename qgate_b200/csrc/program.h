@@ -1,0 +1,83 @@
+/*
+ * program.h — the "pass program" shared by the host planner and the device kernels.
+ *
+ * A deferred run of gates on one state vector is cut into PASSES.  One pass is one
+ * read + one write of the state vector (2 * 2^n * sizeof(complex) algorithmic bytes):
+ * every CTA stages a TILE of 2^T amplitudes in shared memory, applies the pass's gates
+ * to it and writes it back.  The tile is the sub-cube spanned by T "tile lanes": the low
+ * L lanes (contiguous in memory -> coalesced / bulk transfers) plus T-L arbitrary lanes.
+ * Inside a pass the gates are grouped into STAGES; in a stage each thread keeps 2^K
+ * amplitudes (the K "register bits" of the stage) in registers and applies the stage's
+ * gates without touching shared memory.
+ *
+ * This header is plain C++ (no CUDA types) so tests can compile the planner alone.
+ * Reference semantics being reproduced: one applyGate / applyControlledGate per entry,
+ * qgate/simulator/src/CPUQubitProcessor.cpp:307-362.
+ */
+#pragma once
+#include <stdint.h>
+
+namespace qgb {
+
+enum OpKind : int {
+    OP_GEN = 0,      /* full 2x2 on register bit `bit` (index into the stage's R[])          */
+    OP_DIAG = 1,     /* diag(d0, d1) on tile bit `bit`: m[0..1] = d0, m[2..3] = d1            */
+    OP_PHASE = 2,    /* multiply by m[0..1] where all bits of ctrl_tile are set               */
+    OP_DIAG_OUT = 3, /* diag on a lane OUTSIDE the tile (`bit` = state-vector lane): the CTA  */
+                     /* picks d0 or d1 from its base index, then acts like OP_PHASE           */
+    OP_XSWAP = 4,    /* anti-diagonal [[0, m01], [m10, 0]] on register bit `bit`:             */
+                     /* m[0..1] = m01, m[2..3] = m10                                          */
+};
+
+#define QGB_MAX_TILE_LANES 14
+#define QGB_MAX_REG_BITS 4
+#define QGB_MAX_LANES 40
+#define QGB_MAX_STAGES 40
+#define QGB_MAX_OPS 112
+
+template <typename real>
+struct Op {
+    real m[8];            /* (re,im) of m00, m01, m10, m11 in the state precision          */
+    int32_t kind;
+    int32_t bit;
+    uint32_t ctrl_tile;   /* controls inside the tile, tile-bit coordinates                */
+    uint32_t pad_;
+    uint64_t ctrl_out;    /* controls outside the tile, state-vector index coordinates     */
+};
+
+struct Stage {
+    int16_t op_begin, op_end;
+    int8_t R[QGB_MAX_REG_BITS];           /* register bit j  <-> tile bit R[j], ascending   */
+    int8_t W[QGB_MAX_TILE_LANES];         /* thread bit i    <-> tile bit W[i]              */
+};
+
+template <typename real>
+struct PassProgram {
+    int32_t n_lanes;      /* lanes of the (local) state vector                             */
+    int32_t T;            /* tile lanes                                                    */
+    int32_t L;            /* low contiguous lanes inside the tile                          */
+    int32_t K;            /* register bits per stage                                       */
+    int32_t n_stages;
+    int32_t n_ops;
+    int8_t tile_lane[QGB_MAX_TILE_LANES];   /* tile bit p <-> lane, ascending, [p] = p for p < L */
+    int8_t rest_lane[QGB_MAX_LANES];        /* the n_lanes - T other lanes, ascending        */
+    Stage stage[QGB_MAX_STAGES];
+    Op<real> op[QGB_MAX_OPS];
+};
+
+/* one queued gate, always kept in double (glue.cpp:382-405 builds the matrix in double and
+ * the processor casts to the state precision at apply time, CPUQubitProcessor.cpp:312). */
+struct Gate {
+    double m[8];
+    int32_t target;
+    uint64_t ctrl_mask;
+};
+
+inline bool gate_is_diag(const Gate &g) {
+    return g.m[2] == 0. && g.m[3] == 0. && g.m[4] == 0. && g.m[5] == 0.;
+}
+inline bool gate_is_antidiag(const Gate &g) {
+    return g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0.;
+}
+
+} // namespace qgb

@@ -1,0 +1,245 @@
+/*
+ * planner_emul.cpp — CPU test of the flush planner (qgate_b200/csrc/planner.cpp).
+ *
+ * Interprets the pass programs exactly as kernels_tile.cu's tile_pass_kernel does (same tile
+ * gather, same thread/register bit maps, same per-op semantics, ops applied per "thread") on
+ * a host array, and compares with applying the submitted gates one by one in submission
+ * order (the reference semantics, CPUQubitProcessor.cpp:307-362).  Also checks that every
+ * stage's (thread, register) map covers the tile exactly once.
+ *
+ * Test infrastructure only: built and run by tests/test_planner.py, never shipped.
+ */
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "planner.h"
+
+using namespace qgb;
+typedef std::complex<double> cd;
+
+static int g_failures = 0;
+#define CHECK(cond, ...)                      \
+    do {                                      \
+        if (!(cond)) {                        \
+            ++g_failures;                     \
+            std::printf("FAIL: " __VA_ARGS__); \
+            std::printf("\n");                \
+        }                                     \
+    } while (0)
+
+static void apply_direct(std::vector<cd> &amp, int n, const Gate &g) {
+    const cd m00(g.m[0], g.m[1]), m01(g.m[2], g.m[3]), m10(g.m[4], g.m[5]), m11(g.m[6], g.m[7]);
+    const uint64_t tb = 1ull << g.target;
+    for (uint64_t i = 0; i < (1ull << n); ++i) {
+        if (i & tb) continue;
+        if ((i & g.ctrl_mask) != g.ctrl_mask) continue;
+        const cd q0 = amp[i], q1 = amp[i | tb];
+        amp[i] = m00 * q0 + m01 * q1;
+        amp[i | tb] = m10 * q0 + m11 * q1;
+    }
+}
+
+template <typename real>
+static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
+    const int n = p.n_lanes, T = p.T, L = p.L, K = p.K;
+    CHECK(T >= K && L <= T && T <= n, "bad shape n=%d T=%d L=%d K=%d", n, T, L, K);
+    for (int i = 0; i < L; ++i) CHECK(p.tile_lane[i] == i, "low lane %d not in the tile", i);
+    for (int i = 1; i < T; ++i) CHECK(p.tile_lane[i] > p.tile_lane[i - 1], "tile lanes not ascending");
+    const uint32_t tile_size = 1u << T, lowmask = (1u << L) - 1u;
+    std::vector<uint64_t> choff(1u << (T - L));
+    for (uint32_t c = 0; c < choff.size(); ++c) {
+        uint64_t off = 0;
+        for (int b = 0; b < T - L; ++b) off |= (uint64_t)((c >> b) & 1u) << p.tile_lane[L + b];
+        choff[c] = off;
+    }
+    std::vector<cd> tile(tile_size);
+    for (uint64_t bid = 0; bid < (1ull << (n - T)); ++bid) {
+        uint64_t base = 0;
+        for (int i = 0; i < n - T; ++i) base |= ((bid >> i) & 1ull) << p.rest_lane[i];
+        for (uint32_t e = 0; e < tile_size; ++e) tile[e] = amp[base | choff[e >> L] | (e & lowmask)];
+        for (int s = 0; s < p.n_stages; ++s) {
+            const Stage &st = p.stage[s];
+            if (st.op_begin == st.op_end) continue;
+            std::vector<int> seen(tile_size, 0);
+            uint32_t rb[QGB_MAX_REG_BITS];
+            for (int j = 0; j < K; ++j) rb[j] = 1u << st.R[j];
+            for (uint32_t tid = 0; tid < (1u << (T - K)); ++tid) {
+                uint32_t ebase = 0;
+                for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
+                auto roff = [&](int r) {
+                    uint32_t o = 0;
+                    for (int j = 0; j < K; ++j)
+                        if (r & (1 << j)) o |= rb[j];
+                    return o;
+                };
+                std::vector<cd> a(1u << K);
+                for (int r = 0; r < (1 << K); ++r) {
+                    a[r] = tile[ebase | roff(r)];
+                    seen[ebase | roff(r)]++;
+                }
+                for (int o = st.op_begin; o < st.op_end; ++o) {
+                    const Op<real> &op = p.op[o];
+                    if ((base & op.ctrl_out) != op.ctrl_out) continue;
+                    const uint32_t cm = op.ctrl_tile;
+                    const cd m0(op.m[0], op.m[1]), m1(op.m[2], op.m[3]), m2(op.m[4], op.m[5]),
+                        m3(op.m[6], op.m[7]);
+                    if (op.kind == OP_GEN || op.kind == OP_XSWAP) {
+                        CHECK(op.bit >= 0 && op.bit < K, "register bit %d out of range", op.bit);
+                        for (int r0 = 0; r0 < (1 << K); ++r0) {
+                            if (r0 & (1 << op.bit)) continue;
+                            const int r1 = r0 | (1 << op.bit);
+                            const uint32_t e0 = ebase | roff(r0);
+                            if ((e0 & cm) != cm) continue;
+                            const cd q0 = a[r0], q1 = a[r1];
+                            if (op.kind == OP_GEN) {
+                                a[r0] = m0 * q0 + m1 * q1;
+                                a[r1] = m2 * q0 + m3 * q1;
+                            } else if (op.pad_) {
+                                a[r0] = q1;
+                                a[r1] = q0;
+                            } else {
+                                a[r0] = m0 * q1;
+                                a[r1] = m1 * q0;
+                            }
+                        }
+                    } else {
+                        for (int r = 0; r < (1 << K); ++r) {
+                            const uint32_t e = ebase | roff(r);
+                            if ((e & cm) != cm) continue;
+                            if (op.kind == OP_PHASE)
+                                a[r] *= m0;
+                            else if (op.kind == OP_DIAG)
+                                a[r] *= ((e >> op.bit) & 1u) ? m1 : m0;
+                            else if (op.kind == OP_DIAG_OUT)
+                                a[r] *= ((base >> op.bit) & 1ull) ? m1 : m0;
+                            else
+                                CHECK(false, "unknown op kind %d", op.kind);
+                        }
+                    }
+                }
+                for (int r = 0; r < (1 << K); ++r) tile[ebase | roff(r)] = a[r];
+            }
+            for (uint32_t e = 0; e < tile_size; ++e)
+                if (seen[e] != 1) {
+                    CHECK(false, "stage %d covers tile element %u %d times", s, e, seen[e]);
+                    break;
+                }
+        }
+        for (uint32_t e = 0; e < tile_size; ++e) amp[base | choff[e >> L] | (e & lowmask)] = tile[e];
+    }
+}
+
+static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
+    std::uniform_real_distribution<double> u(-3.14159, 3.14159);
+    Gate g;
+    g.target = (int)(rng() % n);
+    g.ctrl_mask = 0;
+    int n_ctrl = (int)(rng() % (max_ctrl + 1));
+    for (int c = 0; c < n_ctrl; ++c) {
+        int lane = (int)(rng() % n);
+        if (lane != g.target) g.ctrl_mask |= 1ull << lane;
+    }
+    for (int i = 0; i < 8; ++i) g.m[i] = 0.;
+    const int kind = (int)(rng() % 6);
+    const double a = u(rng), b = u(rng), c = u(rng);
+    switch (kind) {
+    case 0: /* general unitary */
+    case 1:
+        g.m[0] = std::cos(a) * std::cos(b);  g.m[1] = std::cos(a) * std::sin(b);
+        g.m[2] = -std::sin(a) * std::cos(c); g.m[3] = -std::sin(a) * std::sin(c);
+        g.m[4] = std::sin(a) * std::cos(-c); g.m[5] = std::sin(a) * std::sin(-c);
+        g.m[6] = std::cos(a) * std::cos(-b); g.m[7] = std::cos(a) * std::sin(-b);
+        break;
+    case 2: /* phase (d0 == 1) */
+        g.m[0] = 1.;
+        g.m[6] = std::cos(a); g.m[7] = std::sin(a);
+        break;
+    case 3: /* general diagonal */
+        g.m[0] = std::cos(a); g.m[1] = std::sin(a);
+        g.m[6] = std::cos(b); g.m[7] = std::sin(b);
+        break;
+    case 4: /* X */
+        g.m[2] = 1.; g.m[4] = 1.;
+        break;
+    case 5: /* Y-like anti-diagonal */
+        g.m[2] = std::cos(a); g.m[3] = std::sin(a);
+        g.m[4] = std::cos(b); g.m[5] = std::sin(b);
+        break;
+    }
+    return g;
+}
+
+template <typename real>
+static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops, int max_stages,
+                     bool merge, uint64_t seed) {
+    std::mt19937_64 rng(seed);
+    std::vector<cd> ref(1ull << n), amp;
+    std::normal_distribution<double> nd;
+    for (auto &v : ref) v = cd(nd(rng), nd(rng));
+    amp = ref;
+    std::vector<Gate> queue;
+    int n_merged = 0;
+    for (int i = 0; i < n_gates; ++i) {
+        Gate g = random_gate(rng, n, max_ctrl);
+        apply_direct(ref, n, g);
+        n_merged += enqueue_gate(queue, g, merge) ? 1 : 0;
+    }
+    PlanConfig cfg;
+    cfg.fp32 = sizeof(real) == 4;
+    cfg.K = cfg.fp32 ? 4 : 3;
+    cfg.T = T;
+    cfg.L = L;
+    cfg.max_ops = max_ops;
+    cfg.max_stages = max_stages;
+    static PassProgram<real> prog;
+    int n_pass = 0, n_exec = 0;
+    while (!queue.empty()) {
+        const size_t before = queue.size();
+        PlanStats st;
+        plan_pass<real>(queue, n, cfg, prog, st);
+        CHECK(queue.size() < before, "planner made no progress");
+        if (queue.size() >= before) return;
+        CHECK((int)(before - queue.size()) == st.gates_in_pass, "gate accounting");
+        CHECK(prog.n_ops <= max_ops && prog.n_stages <= std::max(1, max_stages), "limits exceeded");
+        emulate_pass<real>(prog, amp);
+        ++n_pass;
+        n_exec += st.gates_in_pass;
+    }
+    CHECK(n_exec + n_merged == n_gates, "executed %d + merged %d != %d", n_exec, n_merged, n_gates);
+    double err = 0., scale = 0.;
+    for (size_t i = 0; i < ref.size(); ++i) {
+        err = std::max(err, std::abs(ref[i] - amp[i]));
+        scale = std::max(scale, std::abs(ref[i]));
+    }
+    const double tol = sizeof(real) == 4 ? 2e-4 : 1e-11; /* op matrices are rounded to `real` */
+    CHECK(err <= tol * scale, "n=%d T=%d L=%d gates=%d: rel err %.3g", n, T, L, n_gates, err / scale);
+    std::printf("ok %s n=%2d T=%2d L=%d gates=%4d passes=%3d merged=%3d relerr=%.2e\n",
+                sizeof(real) == 4 ? "f32" : "f64", n, T, L, n_gates, n_pass, n_merged, err / scale);
+}
+
+int main() {
+    uint64_t seed = 1;
+    for (int n : {4, 5, 8, 10, 12}) {
+        for (int T : {5, 7, 9, 12}) {
+            for (int L : {1, 3, 5}) {
+                if (T < 4) continue;
+                run_case<double>(n, T, L, 150, 3, QGB_MAX_OPS, QGB_MAX_STAGES, true, seed++);
+                run_case<float>(n, T, L, 60, 2, QGB_MAX_OPS, QGB_MAX_STAGES, true, seed++);
+            }
+        }
+    }
+    /* limits and no-merge paths */
+    run_case<double>(10, 7, 2, 300, 3, 5, QGB_MAX_STAGES, false, seed++);
+    run_case<double>(10, 7, 2, 300, 3, QGB_MAX_OPS, 2, true, seed++);
+    run_case<double>(11, 8, 3, 400, 9, 16, 3, true, seed++);
+    run_case<float>(11, 9, 4, 200, 4, 7, 2, false, seed++);
+    if (g_failures) {
+        std::printf("%d FAILURES\n", g_failures);
+        return 1;
+    }
+    std::printf("ALL OK\n");
+    return 0;
+}

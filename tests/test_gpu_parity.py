@@ -1,0 +1,300 @@
+"""GPU suite: the sm_100a engine, driven through the C ABI by the same host stack, against
+(1) the golden vectors recorded from the real reference (tests/golden/), (2) the unmodified
+reference CPU runtime (oracle/_ref) run on the same seeded inputs, and (3) size-independent
+properties at BASELINE-scale qubit counts.
+
+Tolerances are BASELINE.json's: amplitudes within 1e-12 (complex128) / 1e-5 (complex64)
+relative to max|a|; measurement outcomes and complex128 sampled indices bit-exact for
+identical random draws."""
+import math
+
+import numpy as np
+import pytest
+
+import qgate_b200
+import qgate_b200.script as S
+from qgate_b200 import circuits
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+PREPS = ('dynamic', 'one_static')
+RTS = (('cpu64', np.float64), ('cpu32', np.float32))
+PROB_TOL = {np.float64: 1e-12, np.float32: 2e-6}
+
+
+@pytest.fixture(autouse=True)
+def default_options(cuda_runtime):
+    api = cuda_runtime.get_api()
+    for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 11), ('tile_lanes_fp32', 12),
+                        ('low_lanes_fp64', 5), ('low_lanes_fp32', 6), ('max_gates_per_pass', 112)):
+        api.set_option(name, value)
+    yield
+
+
+@pytest.mark.parametrize('name', sorted(cases.CIRCUITS))
+@pytest.mark.parametrize('prep', PREPS)
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_states_prob_p0_vs_golden(golden, cuda_runtime, name, prep, rt, dtype):
+    sim, q = cases.run_circuit(cuda_runtime, name, dtype, prep)
+    key = '{}/{}/{}'.format(name, prep, rt)
+    states = sim.qubits.states[:]
+    assert states.dtype == golden[key + '/states'].dtype
+    assert cases.rel_err(states, golden[key + '/states']) < cases.TOL[dtype]
+    if dtype is np.float32:  # also against the complex128 reference run
+        assert cases.rel_err(states, golden['{}/{}/cpu64/states'.format(name, prep)]) < 1e-5
+    assert np.abs(sim.qubits.prob[:] - golden[key + '/prob']).max() < PROB_TOL[dtype]
+    p0 = np.array([sim.qubits.calc_probability(qr) for qr in q])
+    assert np.abs(p0 - golden[key + '/p0']).max() < (1e-12 if dtype is np.float64 else 1e-5)
+    assert cuda_runtime.get_api().backend_name == 'cuda-sm_100a'
+
+
+@pytest.mark.parametrize('name', ('rand6x10', 'zoo7', 'grover8', 'ghz11'))
+@pytest.mark.parametrize('prep', PREPS)
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_measure_all_bits_exact(golden, cuda_runtime, name, prep, rt, dtype):
+    sim = cases.make_sim(cuda_runtime, dtype, prep)
+    q, ops = cases.CIRCUITS[name]()
+    refs = S.new_references(len(q))
+    np.random.seed(11)
+    sim.run(ops + [S.measure(r, qr) for r, qr in zip(refs, q)])
+    sim.qubits.set_ordering(q)
+    key = 'measure/{}/{}/{}'.format(name, prep, rt)
+    assert np.array_equal(np.array(sim.values.get(refs), np.int64), golden[key + '/bits'])
+    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype] * 10
+
+
+@pytest.mark.parametrize('prep', PREPS)
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_midcircuit_measure_reset_if(golden, cuda_runtime, prep, rt, dtype):
+    sim = cases.make_sim(cuda_runtime, dtype, prep)
+    q, refs, ops = cases.midcircuit_ops()
+    np.random.seed(5)
+    sim.run(ops)
+    sim.qubits.set_ordering(q)
+    key = 'measure/midcircuit/{}/{}'.format(prep, rt)
+    assert np.array_equal(np.array(sim.values.get(refs), np.int64), golden[key + '/bits'])
+    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype] * 10
+
+
+class Probe:
+    def __init__(self, prob, empty_lanes, qreg_ordering):
+        self.prob = prob
+
+
+@pytest.mark.parametrize('name', ('rand10x20', 'zoo9', 'grover8'))
+@pytest.mark.parametrize('prep', PREPS)
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_sampling_pool_indices(golden, cuda_runtime, name, prep, rt, dtype):
+    rnd = np.random.RandomState(7).random_sample(20000)
+    sim = cases.make_sim(cuda_runtime, dtype, prep)
+    q, ops = cases.CIRCUITS[name]()
+    empty = S.new_qregs(2)
+    sim.run(ops)
+    key = 'sampling/{}/{}/{}'.format(name, prep, rt)
+    orderings = {'full': q, 'hidden': q[1::2],
+                 'empty': [q[3], empty[0], q[0], q[5], empty[1], q[1]],
+                 'reversed': list(reversed(q))}
+    for tag, ordering in orderings.items():
+        got = sim.qubits.create_sampling_pool(ordering).sample(20000, rnd).intarray
+        want = golden[key + '/' + tag]
+        if dtype is np.float64:
+            assert np.array_equal(got, want), tag
+        else:
+            # complex64: the reference accumulates its cumulative sum in float32 (error ~1e-6,
+            # dependent on its worker count); the engine accumulates in float64.  Indices agree
+            # except for draws that fall inside that band.
+            assert np.mean(got == want) > 0.995, (tag, np.mean(got == want))
+    prob = sim.qubits.create_sampling_pool(q[1::2], Probe).prob
+    assert prob.dtype == np.dtype(dtype)
+    assert np.allclose(prob, golden[key + '/prob_hidden'], rtol=1e-12 if dtype is np.float64 else 1e-4,
+                       atol=1e-15 if dtype is np.float64 else 1e-8)
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_sampling_is_searchsorted_of_own_prob_array(cuda_runtime, dtype):
+    """The pool's documented algorithm: inclusive scan in float64 of the marginal probability
+    vector, scaled by 1/total, then upper_bound (CPUSamplingPool.cpp:8-81 in float64)."""
+    sim, q = cases.run_circuit(cuda_runtime, 'rand13x8', dtype, 'one_static')
+    rnd = np.random.RandomState(21).random_sample(50000)
+    got = sim.qubits.create_sampling_pool(q).sample(50000, rnd).intarray
+    prob = sim.qubits.create_sampling_pool(q, Probe).prob.astype(np.float64)
+    cum = np.cumsum(prob)
+    cum *= 1. / cum[-1]
+    r = rnd if dtype is np.float64 else rnd.astype(np.float32).astype(np.float64)
+    want = np.minimum(np.searchsorted(cum, r, side='right'), len(cum) - 1)
+    mismatch = np.flatnonzero(got != want)
+    # a different (tiled) summation order may move a boundary by a few ulps
+    assert len(mismatch) <= 2
+    for i in mismatch:
+        assert abs(int(got[i]) - int(want[i])) == 1
+        assert abs(cum[min(got[i], want[i])] - r[i]) < 1e-13
+
+
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_get_states_slices(golden, cuda_runtime, rt, dtype):
+    sim, q = cases.run_circuit(cuda_runtime, 'rand10x20', dtype, 'dynamic')
+    extra = S.new_qregs(1)
+    tol = cases.TOL[dtype]
+    for idx, k in enumerate(cases.SLICE_KEYS):
+        want = golden['slices/{}/{}/states'.format(rt, idx)]
+        got = sim.qubits.states[slice(*k)]
+        assert got.shape == want.shape, k
+        if want.size:
+            assert np.abs(got - want).max() < tol, k
+        wantp = golden['slices/{}/{}/prob'.format(rt, idx)]
+        gotp = sim.qubits.prob[slice(*k)]
+        assert gotp.shape == wantp.shape
+        if wantp.size:
+            assert np.abs(gotp - wantp).max() < tol, k
+    sim.qubits.set_ordering(q[:4] + extra + q[4:])
+    want = golden['slices/{}/empty_lane/states'.format(rt)]
+    assert np.abs(sim.qubits.states[::5] - want).max() < tol
+    sim.qubits.set_ordering(q)
+    with pytest.raises(RuntimeError):
+        sim.qubits.states[1 << 10]
+
+
+@pytest.mark.parametrize('rt,dtype', RTS)
+def test_phase_estimation_hidden_target(golden, cuda_runtime, rt, dtype):
+    sim = cases.make_sim(cuda_runtime, dtype, 'dynamic')
+    bits, target, ops = circuits.phase_estimation(S, 8, 0.1)
+    sim.run(ops)
+    sim.qubits.set_ordering(bits + [target])
+    assert cases.rel_err(sim.qubits.states[:], golden['pe8/{}/states'.format(rt)]) < cases.TOL[dtype]
+    rnd = np.random.RandomState(3).random_sample(4096)
+    got = sim.qubits.create_sampling_pool(bits).sample(4096, rnd).intarray
+    if dtype is np.float64:
+        assert np.array_equal(got, golden['pe8/{}/samples'.format(rt)])
+    else:
+        assert np.mean(got == golden['pe8/{}/samples'.format(rt)]) > 0.995
+
+
+def test_qft20_config0(golden, cuda_runtime):
+    """BASELINE.json configs[0]: 20-qubit QFT, complex128."""
+    sim = cases.make_sim(cuda_runtime, np.float64, 'one_static')
+    q, ops = circuits.qft(S, 20)
+    sim.run(ops)
+    sim.qubits.set_ordering(q)
+    scale = 2. ** -10
+    assert np.abs(sim.qubits.states[::4099] - golden['qft20/cpu64/states_stride4099']).max() < 1e-12 * scale
+    assert np.abs(sim.qubits.states[:512] - golden['qft20/cpu64/states_head']).max() < 1e-12 * scale
+    for qr in q:
+        assert abs(sim.qubits.calc_probability(qr) - 0.5) < 1e-12
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+@pytest.mark.parametrize('gen', ('random', 'zoo', 'grover', 'qft'))
+def test_against_reference_cpu_runtime_16_to_20_qubits(cuda_runtime, ref_runtime, dtype, gen):
+    """Same seeded circuit on the engine and on the unmodified reference CPU runtime."""
+    def build():
+        if gen == 'random':
+            return circuits.random_u3_cx(S, 20, 6, seed=77)
+        if gen == 'zoo':
+            return circuits.mixed_gate_zoo(S, 16, 600, seed=9)
+        if gen == 'grover':
+            return circuits.grover(S, 18, 3, 0x2AAAA)
+        return circuits.qft(S, 19)
+    q, ops = build()
+    refs = S.new_references(3)
+    tail = [S.measure(refs[0], q[2]), S.measure(refs[1], q[len(q) - 1]), S.H(q[2]),
+            S.measure(refs[2], q[2])]
+    outs = []
+    for rt in (cuda_runtime, ref_runtime.module):
+        sim = cases.make_sim(rt, dtype, 'one_static')
+        np.random.seed(123)
+        sim.run(ops + tail)
+        sim.qubits.set_ordering(q)
+        p0 = [sim.qubits.calc_probability(qr) for qr in q]
+        rnd = np.random.RandomState(4).random_sample(100000)
+        samples = sim.qubits.create_sampling_pool(q).sample(100000, rnd).intarray
+        outs.append((sim.qubits.states[:], sim.values.get(refs), np.array(p0), samples))
+        sim.terminate()
+    (a, bits_a, p0_a, s_a), (b, bits_b, p0_b, s_b) = outs
+    assert bits_a == bits_b
+    assert cases.rel_err(a, b) < cases.TOL[dtype]
+    assert np.abs(p0_a - p0_b).max() < (1e-12 if dtype is np.float64 else 1e-5)
+    if dtype is np.float64:
+        assert np.array_equal(s_a, s_b)
+    else:
+        assert np.mean(s_a == s_b) > 0.99
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
+    """The planner may only reorder commuting gates: every tile shape, and the one-kernel-per-gate
+    path, must give the same amplitudes."""
+    api = cuda_runtime.get_api()
+    q, ops = circuits.mixed_gate_zoo(S, 15, 500, seed=31)
+    q2, ops2 = circuits.random_u3_cx(S, 15, 12, seed=8, qregs=q)
+    ops = ops + ops2
+
+    def run(**options):
+        for k, v in options.items():
+            api.set_option(k, v)
+        sim = cases.make_sim(cuda_runtime, dtype, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        out = sim.qubits.states[:]
+        sim.terminate()
+        return out
+
+    base = run(fuse=0)
+    tol = 1e-13 if dtype is np.float64 else 2e-6
+    shapes = [dict(fuse=1, merge=0), dict(fuse=1, merge=1)]
+    lanes = 'tile_lanes_fp64' if dtype is np.float64 else 'tile_lanes_fp32'
+    low = 'low_lanes_fp64' if dtype is np.float64 else 'low_lanes_fp32'
+    k = 3 if dtype is np.float64 else 4
+    for t in (k + 5, k + 6, k + 8, k + 9, k + 10):
+        for l in (1, 3, 6):
+            shapes.append({'fuse': 1, lanes: t, low: l})
+    shapes.append(dict(fuse=1, max_gates_per_pass=3))
+    for options in shapes:
+        got = run(**options)
+        assert cases.rel_err(got, base) < tol, options
+
+
+@pytest.mark.parametrize('dtype,n', ((np.float64, 27), (np.float32, 28)))
+def test_large_state_properties(cuda_runtime, dtype, n):
+    """BASELINE-scale checks that need no oracle: norm, per-qubit probabilities and amplitude
+    slices of QFT|x> against the closed form, U followed by U^dagger returning |0...0>."""
+    sim = cases.make_sim(cuda_runtime, dtype, 'one_static')
+    q, ops = circuits.qft(S, n)     # X(q0) X(q2) -> |x=5>, then QFT
+    sim.run(ops)
+    sim.qubits.set_ordering(q)
+    tol = cases.TOL[dtype]
+    amp = 2. ** (-n / 2.)
+    # QFT without the final swaps on |x>, x = 5 (q0 is the LSB): amplitude of |k> is
+    # exp(2 pi i k rev_n(x) / 2^n) / sqrt(2^n); validated against the reference CPU runtime at
+    # 9 and 12 qubits (max |diff| 1.4e-17).
+    start, step = 12345, 65537
+    got = sim.qubits.states[start::step]
+    ks = np.arange(start, 1 << n, step, dtype=np.int64)
+    xr = (1 << (n - 1)) + (1 << (n - 3))
+    phase = (ks * xr) % (1 << n)
+    want = amp * np.exp(2j * np.pi * phase.astype(np.float64) / float(1 << n))
+    assert np.abs(got - want).max() < tol * amp * (4 if dtype is np.float32 else 1)
+    for qr in (q[0], q[5], q[n // 2], q[n - 1]):
+        assert abs(sim.qubits.calc_probability(qr) - 0.5) < (1e-12 if dtype is np.float64 else 1e-5)
+    # inverse: all gates adjointed in reverse order
+    inverse = []
+    for i in range(n):
+        inverse.append(S.H(q[i]))
+        for j in range(i + 1, n):
+            inverse.append(S.ctrl(q[j]).U1(-math.pi / float(1 << (j - i)))(q[i]))
+    sim.run(list(reversed(inverse)))
+    head = sim.qubits.states[:8]
+    assert abs(abs(head[5]) - 1.) < (1e-11 if dtype is np.float64 else 2e-5)
+    assert np.abs(np.delete(head, 5)).max() < (1e-11 if dtype is np.float64 else 2e-5)
+    sim.terminate()
+
+
+def test_errors_surface_as_exceptions(cuda_runtime):
+    api = cuda_runtime.get_api()
+    with pytest.raises(ValueError):
+        api.call('qgb_qstates_delete', 12345)
+    sim = cases.make_sim(cuda_runtime, np.float64, 'dynamic')
+    q = S.new_qregs(3)
+    sim.run([S.H(q[0]), S.ctrl(q[0]).X(q[1])])
+    with pytest.raises(RuntimeError):
+        sim.run([S.reset(q[1])])   # not measured (rop_executor.py:45-51)
