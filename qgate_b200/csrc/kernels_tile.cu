@@ -42,19 +42,23 @@ template <int K> __device__ __forceinline__ uint32_t reg_offset(int r, const uin
     return off;
 }
 
-/* ---- per-op bodies; `a` is the thread's register file of 2^K amplitudes ---------------- */
+/* ---- per-op bodies; `a` is the thread's register file of 2^K amplitudes -----------------
+ * Every predicate inside an op body is UNIFORM (the same for all threads: it depends on the
+ * op and the register index only); the per-thread part of the control predicate is tested
+ * once, before the body.  This keeps the amplitudes in fixed registers across the op loop:
+ * with per-amplitude divergent predicates ptxas copied the whole register file (32 MOVs)
+ * on every op (profiles/r1a_tile_f64_summary.md). */
 
 template <typename real, int K, int J>
 __device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K], const real *m,
-                                          uint32_t cm, uint32_t ebase, const uint32_t (&rb)[K]) {
+                                          uint32_t regmask) {
     const real m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3];
     const real m10r = m[4], m10i = m[5], m11r = m[6], m11i = m[7];
 #pragma unroll
     for (int r0 = 0; r0 < (1 << K); ++r0) {
         if (r0 & (1 << J)) continue;
         const int r1 = r0 | (1 << J);
-        const uint32_t e0 = ebase | reg_offset<K>(r0, rb);
-        if ((e0 & cm) == cm) {
+        if (regmask & (1u << r0)) {
             const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
             a[r0].x = m00r * q0r - m00i * q0i + m01r * q1r - m01i * q1i;
             a[r0].y = m00r * q0i + m00i * q0r + m01r * q1i + m01i * q1r;
@@ -65,37 +69,29 @@ __device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K]
 }
 
 template <typename real, int K, int J>
-__device__ __forceinline__ void apply_xswap(typename Cplx<real>::type (&a)[1 << K], const real *m,
-                                            bool pure_swap, uint32_t cm, uint32_t ebase,
-                                            const uint32_t (&rb)[K]) {
-    const real m01r = m[0], m01i = m[1], m10r = m[2], m10i = m[3];
+__device__ __forceinline__ void apply_swap(typename Cplx<real>::type (&a)[1 << K], uint32_t regmask,
+                                           bool active) {
 #pragma unroll
     for (int r0 = 0; r0 < (1 << K); ++r0) {
         if (r0 & (1 << J)) continue;
         const int r1 = r0 | (1 << J);
-        const uint32_t e0 = ebase | reg_offset<K>(r0, rb);
-        if ((e0 & cm) == cm) {
-            const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
-            if (pure_swap) {
-                a[r0].x = q1r; a[r0].y = q1i;
-                a[r1].x = q0r; a[r1].y = q0i;
-            } else {
-                a[r0].x = m01r * q1r - m01i * q1i;
-                a[r0].y = m01r * q1i + m01i * q1r;
-                a[r1].x = m10r * q0r - m10i * q0i;
-                a[r1].y = m10r * q0i + m10i * q0r;
-            }
+        if (regmask & (1u << r0)) {
+            const typename Cplx<real>::type t0 = a[r0], t1 = a[r1];
+            a[r0].x = active ? t1.x : t0.x;
+            a[r0].y = active ? t1.y : t0.y;
+            a[r1].x = active ? t0.x : t1.x;
+            a[r1].y = active ? t0.y : t1.y;
         }
     }
 }
 
+/* the same factor (dr, di), per thread, on every selected register */
 template <typename real, int K>
 __device__ __forceinline__ void apply_phase(typename Cplx<real>::type (&a)[1 << K], real dr, real di,
-                                            uint32_t cm, uint32_t ebase, const uint32_t (&rb)[K]) {
+                                            uint32_t regmask) {
 #pragma unroll
     for (int r = 0; r < (1 << K); ++r) {
-        const uint32_t e = ebase | reg_offset<K>(r, rb);
-        if ((e & cm) == cm) {
+        if (regmask & (1u << r)) {
             const real qr = a[r].x, qi = a[r].y;
             a[r].x = dr * qr - di * qi;
             a[r].y = dr * qi + di * qr;
@@ -103,60 +99,45 @@ __device__ __forceinline__ void apply_phase(typename Cplx<real>::type (&a)[1 << 
     }
 }
 
-template <typename real, int K>
-__device__ __forceinline__ void apply_diag(typename Cplx<real>::type (&a)[1 << K], const real *m,
-                                           uint32_t tbit, uint32_t cm, uint32_t ebase,
-                                           const uint32_t (&rb)[K]) {
-    const real d0r = m[0], d0i = m[1], d1r = m[2], d1i = m[3];
-#pragma unroll
-    for (int r = 0; r < (1 << K); ++r) {
-        const uint32_t e = ebase | reg_offset<K>(r, rb);
-        if ((e & cm) == cm) {
-            const bool one = (e >> tbit) & 1u;
-            const real dr = one ? d1r : d0r, di = one ? d1i : d0i;
-            const real qr = a[r].x, qi = a[r].y;
-            a[r].x = dr * qr - di * qi;
-            a[r].y = dr * qi + di * qr;
-        }
-    }
-}
-
+/* One op.  There is NO thread-divergent branch in here: a thread whose thread-bit controls
+ * are not satisfied runs the same instructions with the identity substituted (matrix,
+ * factor or exchange), so the op loop stays uniform and its parameters stay in uniform
+ * registers. */
 template <typename real, int K>
 __device__ __forceinline__ void apply_op(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
-                                         uint64_t base, uint32_t ebase, const uint32_t (&rb)[K]) {
+                                         uint64_t base, uint32_t ebase) {
     /* controls outside the tile are the same for the whole CTA */
     if ((base & op.ctrl_out) != op.ctrl_out) return;
-    const uint32_t cm = op.ctrl_tile;
-    switch (op.kind) {
-    case OP_GEN:
-        switch (op.bit) {
-        case 0: apply_gen<real, K, 0>(a, op.m, cm, ebase, rb); break;
-        case 1: if (K > 1) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, op.m, cm, ebase, rb); break;
-        case 2: if (K > 2) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, op.m, cm, ebase, rb); break;
-        case 3: if (K > 3) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, op.m, cm, ebase, rb); break;
+    const bool active = (ebase & op.cmt) == op.cmt;
+    const uint32_t regmask = op.regmask;
+    const int kind = op.kind, bit = op.bit;
+    if (kind == OP_GEN) {
+        real m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = active ? op.m[i] : ((i == 0 || i == 6) ? (real)1 : (real)0);
+        if (bit == 0) apply_gen<real, K, 0>(a, m, regmask);
+        if (K > 1 && bit == 1) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, m, regmask);
+        if (K > 2 && bit == 2) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, m, regmask);
+        if (K > 3 && bit == 3) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, m, regmask);
+    } else if (kind == OP_SWAP) {
+        if (bit == 0) apply_swap<real, K, 0>(a, regmask, active);
+        if (K > 1 && bit == 1) apply_swap<real, K, (K > 1 ? 1 : 0)>(a, regmask, active);
+        if (K > 2 && bit == 2) apply_swap<real, K, (K > 2 ? 2 : 0)>(a, regmask, active);
+        if (K > 3 && bit == 3) apply_swap<real, K, (K > 3 ? 3 : 0)>(a, regmask, active);
+    } else {
+        const real d0r = active ? op.m[0] : (real)1, d0i = active ? op.m[1] : (real)0;
+        const real d1r = active ? op.m[2] : (real)1, d1i = active ? op.m[3] : (real)0;
+        const uint32_t regsel = op.regsel;
+        if (regsel != 0) {
+            /* target on a register bit: d1 on the registers of regsel, d0 on the others */
+            apply_phase<real, K>(a, d0r, d0i, regmask & ~regsel);
+            apply_phase<real, K>(a, d1r, d1i, regmask & regsel);
+        } else {
+            /* target on a thread bit (OP_DIAG), outside the tile (OP_DIAG_OUT), or a phase */
+            bool one = (ebase & op.tsel) != 0;
+            if (kind == OP_DIAG_OUT) one = (base >> bit) & 1ull;
+            apply_phase<real, K>(a, one ? d1r : d0r, one ? d1i : d0i, regmask);
         }
-        break;
-    case OP_XSWAP: {
-        const bool pure = op.pad_ != 0;
-        switch (op.bit) {
-        case 0: apply_xswap<real, K, 0>(a, op.m, pure, cm, ebase, rb); break;
-        case 1: if (K > 1) apply_xswap<real, K, (K > 1 ? 1 : 0)>(a, op.m, pure, cm, ebase, rb); break;
-        case 2: if (K > 2) apply_xswap<real, K, (K > 2 ? 2 : 0)>(a, op.m, pure, cm, ebase, rb); break;
-        case 3: if (K > 3) apply_xswap<real, K, (K > 3 ? 3 : 0)>(a, op.m, pure, cm, ebase, rb); break;
-        }
-        break;
-    }
-    case OP_PHASE:
-        apply_phase<real, K>(a, op.m[0], op.m[1], cm, ebase, rb);
-        break;
-    case OP_DIAG:
-        apply_diag<real, K>(a, op.m, (uint32_t)op.bit, cm, ebase, rb);
-        break;
-    case OP_DIAG_OUT: {
-        const bool one = (base >> op.bit) & 1ull;
-        apply_phase<real, K>(a, one ? op.m[2] : op.m[0], one ? op.m[3] : op.m[1], cm, ebase, rb);
-        break;
-    }
     }
 }
 
@@ -224,7 +205,7 @@ tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
 #pragma unroll
         for (int r = 0; r < (1 << K); ++r) a[r] = tile[swz<real>(ebase | reg_offset<K>(r, rb))];
 
-        for (int o = st.op_begin; o < st.op_end; ++o) apply_op<real, K>(a, prog.op[o], base, ebase, rb);
+        for (int o = st.op_begin; o < st.op_end; ++o) apply_op<real, K>(a, prog.op[o], base, ebase);
 
 #pragma unroll
         for (int r = 0; r < (1 << K); ++r) tile[swz<real>(ebase | reg_offset<K>(r, rb))] = a[r];

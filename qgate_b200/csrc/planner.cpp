@@ -228,49 +228,70 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             prog.stage[cur_stage].op_begin = (int16_t)n_ops;
         }
         Op<real> &op = prog.op[n_ops++];
+        const Stage &st = prog.stage[pk.stage];
         const uint64_t ctrl_in = g.ctrl_mask & S;
         op.ctrl_out = g.ctrl_mask & ~S;
-        op.ctrl_tile = 0;
+        uint32_t ct = 0; /* controls inside the tile, tile-bit coordinates */
         for (int lane = 0; lane < n; ++lane)
-            if (ctrl_in & (1ull << lane)) op.ctrl_tile |= 1u << lane_to_tile[lane];
+            if (ctrl_in & (1ull << lane)) ct |= 1u << lane_to_tile[lane];
         const bool in_tile = (S >> g.target) & 1ull;
-        const Stage &st = prog.stage[pk.stage];
         auto regbit = [&](int lane) {
             int tb = lane_to_tile[lane];
             for (int j = 0; j < K; ++j)
                 if (st.R[j] == tb) return j;
             return -1;
         };
+        op.tsel = 0;
+        op.regsel = 0;
+        op.bit = 0;
         if (gate_is_diag(g)) {
             const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
-                op.kind = OP_PHASE;
+                /* phase gate: the target acts as one more control */
+                op.kind = OP_DIAG;
                 if (in_tile)
-                    op.ctrl_tile |= 1u << lane_to_tile[g.target];
+                    ct |= 1u << lane_to_tile[g.target];
                 else
                     op.ctrl_out |= 1ull << g.target;
-                op.m[0] = (real)g.m[6];
-                op.m[1] = (real)g.m[7];
+                op.m[0] = op.m[2] = (real)g.m[6];
+                op.m[1] = op.m[3] = (real)g.m[7];
             } else {
                 op.kind = in_tile ? OP_DIAG : OP_DIAG_OUT;
-                op.bit = in_tile ? lane_to_tile[g.target] : g.target;
                 op.m[0] = (real)g.m[0];
                 op.m[1] = (real)g.m[1];
                 op.m[2] = (real)g.m[6];
                 op.m[3] = (real)g.m[7];
+                if (in_tile) {
+                    const int j = regbit(g.target);
+                    if (j >= 0) {
+                        for (int r = 0; r < (1 << K); ++r)
+                            if (r & (1 << j)) op.regsel |= 1u << r;
+                    } else {
+                        op.tsel = 1u << lane_to_tile[g.target];
+                    }
+                } else {
+                    op.bit = g.target;
+                }
             }
-        } else if (gate_is_antidiag(g)) {
-            op.kind = OP_XSWAP;
+        } else if (g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
+                   g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.) {
+            op.kind = OP_SWAP;
             op.bit = regbit(g.target);
-            op.m[0] = (real)g.m[2];
-            op.m[1] = (real)g.m[3];
-            op.m[2] = (real)g.m[4];
-            op.m[3] = (real)g.m[5];
-            op.pad_ = (g.m[2] == 1. && g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.) ? 1u : 0u;
         } else {
             op.kind = OP_GEN;
             op.bit = regbit(g.target);
             for (int e = 0; e < 8; ++e) op.m[e] = (real)g.m[e];
+        }
+        /* split the in-tile control predicate into its thread part and its register part */
+        uint32_t rmask = 0;
+        for (int j = 0; j < K; ++j) rmask |= 1u << st.R[j];
+        op.cmt = ct & ~rmask;
+        op.regmask = 0;
+        for (int r = 0; r < (1 << K); ++r) {
+            uint32_t roff = 0;
+            for (int j = 0; j < K; ++j)
+                if (r & (1 << j)) roff |= 1u << st.R[j];
+            if ((roff & ct & rmask) == (ct & rmask)) op.regmask |= 1u << r;
         }
     }
     if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;

@@ -21,12 +21,12 @@ namespace qgb {
 
 enum OpKind : int {
     OP_GEN = 0,      /* full 2x2 on register bit `bit` (index into the stage's R[])          */
-    OP_DIAG = 1,     /* diag(d0, d1) on tile bit `bit`: m[0..1] = d0, m[2..3] = d1            */
-    OP_PHASE = 2,    /* multiply by m[0..1] where all bits of ctrl_tile are set               */
+    OP_DIAG = 1,     /* multiply by d1 where the target bit is 1, by d0 elsewhere:           */
+                     /* m[0..1] = d0, m[2..3] = d1.  A phase gate (d0 == 1) is encoded with  */
+                     /* the target folded into the controls and d0 = d1 = the phase.         */
     OP_DIAG_OUT = 3, /* diag on a lane OUTSIDE the tile (`bit` = state-vector lane): the CTA  */
-                     /* picks d0 or d1 from its base index, then acts like OP_PHASE           */
-    OP_XSWAP = 4,    /* anti-diagonal [[0, m01], [m10, 0]] on register bit `bit`:             */
-                     /* m[0..1] = m01, m[2..3] = m10                                          */
+                     /* picks d0 or d1 from its base index                                    */
+    OP_SWAP = 5,     /* exchange the two amplitudes of register bit `bit` (X, CX, CCX ...)    */
 };
 
 #define QGB_MAX_TILE_LANES 14
@@ -35,13 +35,19 @@ enum OpKind : int {
 #define QGB_MAX_STAGES 40
 #define QGB_MAX_OPS 112
 
+/* One op of a stage.  The control predicate of an amplitude with tile index e = ebase | roff(r)
+ * (thread part | register part) is split on the host: `cmt` is tested once per thread,
+ * `regmask` once per register index and is the same for every thread. */
 template <typename real>
 struct Op {
     real m[8];            /* (re,im) of m00, m01, m10, m11 in the state precision          */
     int32_t kind;
     int32_t bit;
-    uint32_t ctrl_tile;   /* controls inside the tile, tile-bit coordinates                */
-    uint32_t pad_;
+    uint32_t cmt;         /* controls on thread bits, tile-bit coordinates                 */
+    uint32_t regmask;     /* bit r set: register index r satisfies the register-bit        */
+                          /* controls (GEN / SWAP: tested for the pair's low index)        */
+    uint32_t tsel;        /* OP_DIAG: tile-bit mask of the target when it is a thread bit  */
+    uint32_t regsel;      /* OP_DIAG: register indices whose target bit is 1               */
     uint64_t ctrl_out;    /* controls outside the tile, state-vector index coordinates     */
 };
 

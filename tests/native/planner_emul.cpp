@@ -80,44 +80,47 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     a[r] = tile[ebase | roff(r)];
                     seen[ebase | roff(r)]++;
                 }
+                uint32_t rmask = 0;
+                for (int j = 0; j < K; ++j) rmask |= rb[j];
                 for (int o = st.op_begin; o < st.op_end; ++o) {
                     const Op<real> &op = p.op[o];
                     if ((base & op.ctrl_out) != op.ctrl_out) continue;
-                    const uint32_t cm = op.ctrl_tile;
+                    CHECK((op.cmt & rmask) == 0, "thread-part controls overlap the register bits");
+                    const bool active = (ebase & op.cmt) == op.cmt;
                     const cd m0(op.m[0], op.m[1]), m1(op.m[2], op.m[3]), m2(op.m[4], op.m[5]),
                         m3(op.m[6], op.m[7]);
-                    if (op.kind == OP_GEN || op.kind == OP_XSWAP) {
+                    if (op.kind == OP_GEN || op.kind == OP_SWAP) {
                         CHECK(op.bit >= 0 && op.bit < K, "register bit %d out of range", op.bit);
                         for (int r0 = 0; r0 < (1 << K); ++r0) {
                             if (r0 & (1 << op.bit)) continue;
                             const int r1 = r0 | (1 << op.bit);
-                            const uint32_t e0 = ebase | roff(r0);
-                            if ((e0 & cm) != cm) continue;
+                            if (!((op.regmask >> r0) & 1u) || !active) continue;
                             const cd q0 = a[r0], q1 = a[r1];
                             if (op.kind == OP_GEN) {
                                 a[r0] = m0 * q0 + m1 * q1;
                                 a[r1] = m2 * q0 + m3 * q1;
-                            } else if (op.pad_) {
+                            } else {
                                 a[r0] = q1;
                                 a[r1] = q0;
-                            } else {
-                                a[r0] = m0 * q1;
-                                a[r1] = m1 * q0;
                             }
                         }
-                    } else {
+                    } else if (op.kind == OP_DIAG || op.kind == OP_DIAG_OUT) {
+                        CHECK(op.kind == OP_DIAG || (op.tsel == 0 && op.regsel == 0), "DIAG_OUT with tile target");
+                        CHECK(op.tsel == 0 || op.regsel == 0, "diag target both thread and register bit");
+                        CHECK((op.tsel & rmask) == 0, "diag thread target overlaps the register bits");
                         for (int r = 0; r < (1 << K); ++r) {
-                            const uint32_t e = ebase | roff(r);
-                            if ((e & cm) != cm) continue;
-                            if (op.kind == OP_PHASE)
-                                a[r] *= m0;
-                            else if (op.kind == OP_DIAG)
-                                a[r] *= ((e >> op.bit) & 1u) ? m1 : m0;
-                            else if (op.kind == OP_DIAG_OUT)
-                                a[r] *= ((base >> op.bit) & 1ull) ? m1 : m0;
+                            if (!((op.regmask >> r) & 1u) || !active) continue;
+                            bool one;
+                            if (op.kind == OP_DIAG_OUT)
+                                one = (base >> op.bit) & 1ull;
+                            else if (op.regsel)
+                                one = (op.regsel >> r) & 1u;
                             else
-                                CHECK(false, "unknown op kind %d", op.kind);
+                                one = (ebase & op.tsel) != 0;
+                            a[r] *= one ? m1 : m0;
                         }
+                    } else {
+                        CHECK(false, "unknown op kind %d", op.kind);
                     }
                 }
                 for (int r = 0; r < (1 << K); ++r) tile[ebase | roff(r)] = a[r];

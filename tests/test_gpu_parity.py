@@ -111,6 +111,28 @@ def test_sampling_pool_indices(golden, cuda_runtime, name, prep, rt, dtype):
                        atol=1e-15 if dtype is np.float64 else 1e-8)
 
 
+def assert_fp32_samples_within_reference_band(got, want, ref_prob32, rnd):
+    """complex64 pools.  The reference builds its cumulative array with a SEQUENTIAL float32
+    running sum per worker (CPUSamplingPool.cpp:17-23), whose rounding error at 2^20 bins is
+    several bin widths and depends on the worker count; the engine scans in float64.  So the
+    indices cannot be identical; what must hold is that every draw lands within the reference's
+    own float32 accumulation band of the reference's answer."""
+    cum64 = np.cumsum(ref_prob32.astype(np.float64))
+    cum64 *= 1. / cum64[-1]
+    cum32 = np.cumsum(ref_prob32, dtype=np.float32).astype(np.float64)
+    cum32 *= 1. / cum32[-1]
+    band = 4. * np.abs(cum32 - cum64).max() + 4. * np.finfo(np.float32).eps
+    r = rnd.astype(np.float32).astype(np.float64)
+    last = len(cum64) - 1
+    # the engine's answer is the exact (float64) upper bound of its own complex64 state, whose
+    # probabilities differ from the reference's by float32 amplitude rounding only ...
+    exact = np.minimum(np.searchsorted(cum64, r, side='right'), last)
+    assert np.mean(got == exact) > 0.99
+    # ... and the reference's answer is never further away than its own rounding band
+    mism = np.flatnonzero(got != want)
+    assert np.abs(cum64[got[mism]] - cum64[want[mism]]).max(initial=0.) <= band, band
+
+
 @pytest.mark.parametrize('dtype', (np.float64, np.float32))
 def test_sampling_is_searchsorted_of_own_prob_array(cuda_runtime, dtype):
     """The pool's documented algorithm: inclusive scan in float64 of the marginal probability
@@ -208,16 +230,17 @@ def test_against_reference_cpu_runtime_16_to_20_qubits(cuda_runtime, ref_runtime
         p0 = [sim.qubits.calc_probability(qr) for qr in q]
         rnd = np.random.RandomState(4).random_sample(100000)
         samples = sim.qubits.create_sampling_pool(q).sample(100000, rnd).intarray
-        outs.append((sim.qubits.states[:], sim.values.get(refs), np.array(p0), samples))
+        prob = sim.qubits.create_sampling_pool(q, Probe).prob
+        outs.append((sim.qubits.states[:], sim.values.get(refs), np.array(p0), samples, prob))
         sim.terminate()
-    (a, bits_a, p0_a, s_a), (b, bits_b, p0_b, s_b) = outs
+    (a, bits_a, p0_a, s_a, prob_a), (b, bits_b, p0_b, s_b, prob_b) = outs
     assert bits_a == bits_b
     assert cases.rel_err(a, b) < cases.TOL[dtype]
     assert np.abs(p0_a - p0_b).max() < (1e-12 if dtype is np.float64 else 1e-5)
     if dtype is np.float64:
         assert np.array_equal(s_a, s_b)
     else:
-        assert np.mean(s_a == s_b) > 0.99
+        assert_fp32_samples_within_reference_band(s_a, s_b, prob_b, rnd)
 
 
 @pytest.mark.parametrize('dtype', (np.float64, np.float32))
