@@ -184,6 +184,53 @@ int qgb_getter_create_sampling_pool(qgb_handle getter,
 int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *randnum);
 int qgb_pool_delete(qgb_handle pool);                           /* glue.cpp:591-602 */
 
+/* ---- sharding support ------------------------------------------------------------
+ * The reference shares the chunks of one state vector between the devices of ONE
+ * process through peer pointers (MultiChunkPtr.h:22-41, CUDADevice.cpp:135-142).  Here one
+ * process drives one GPU and owns one shard of 2^(n - g) amplitudes (the g high-order
+ * "global" lanes select the rank); the host layer (qgate_b200/dist.py) moves lanes between
+ * the shards.  These entry points are what it needs from the native layer. */
+
+/* address of the amplitude array (device memory for the CUDA library, host memory for the
+ * CPU shim) and its size; queued gates are flushed first. */
+int qgb_qstates_data_ptr(qgb_handle qstates, uint64_t *ptr, int64_t *bytes);
+/* a second buffer of the same size (allocated on first use) for out-of-place exchanges,
+ * and the switch that makes it the amplitude array (the old array becomes the spare). */
+int qgb_qstates_alt_buffer(qgb_handle qstates, uint64_t *ptr);
+int qgb_qstates_flip(qgb_handle qstates);
+/* sum of |a|^2 over this array (a shard's share of the norm). */
+int qgb_qproc_calc_norm(qgb_handle qproc, qgb_handle qstates, double *norm);
+/* join for a sharded destination: dst holds elements [index_offset, index_offset + 2^n_dst)
+ * of the n_total_lanes-lane Kronecker product that qgb_qproc_join would build. */
+int qgb_qproc_join_shard(qgb_handle qproc, qgb_handle dst, const qgb_handle *src_list, int n_src,
+                         int n_new_lanes, int n_total_lanes, int64_t index_offset);
+/* two-step sampling pool for a sharded probability vector: `partial` builds the local
+ * (un-normalised) inclusive scan and reports its total; `finalize` turns it into
+ * cum[i] = (offset + scan[i]) / total, where offset is the sum of the totals of the
+ * lower ranks and total the global sum.  A pool made this way deposits no empty lanes. */
+int qgb_getter_create_sampling_pool_partial(qgb_handle getter,
+                                            const int *lane_tables, const int *n_lanes_per_qstates,
+                                            const qgb_handle *qstates_list, int n_qstates,
+                                            int n_lanes, int n_hidden_lanes,
+                                            qgb_handle *pool, double *local_total);
+int qgb_pool_finalize(qgb_handle pool, double offset, double total);
+/* pool over an explicit probability vector of 2^n_lanes doubles in host memory. */
+int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes,
+                             const int *empty_lanes, int n_empty_lanes, qgb_handle *pool);
+/* CUDA IPC: export the allocation behind a qstates (64-byte cudaIpcMemHandle_t + the
+ * offset of the array inside it), map / unmap a peer's export in this process. */
+int qgb_qstates_ipc_export(qgb_handle qstates, void *handle64, int64_t *offset);
+int qgb_ipc_open(const void *handle64, uint64_t *base_ptr);
+int qgb_ipc_close(uint64_t base_ptr);
+/* in-place exchange of k global lanes with the k local lanes victim_lanes[] (ascending):
+ * peer_ptrs[j] (j in [0, 2^k)) is the mapped amplitude array of the rank whose selected
+ * global bits equal j; my_sel is this rank's own value.  Amplitude i of this shard whose
+ * victim bits are j != my_sel trades places with amplitude i' of rank j whose victim bits
+ * are my_sel.  One kernel over peer memory; the caller provides the cross-rank ordering
+ * (all ranks idle on this state before and after). */
+int qgb_qstates_exchange_p2p(qgb_handle qstates, const uint64_t *peer_ptrs, int k,
+                             const int *victim_lanes, int my_sel);
+
 /* ---- instrumentation (no reference counterpart) --------------------------- */
 
 typedef struct qgb_stats {

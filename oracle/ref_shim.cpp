@@ -25,8 +25,13 @@
 #include "CPUQubitProcessor.h"
 #include "CPUQubitsStatesGetter.h"
 
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -110,6 +115,76 @@ qgb_stats g_stats;
 
 } // namespace
 
+/* ---- sharding support: what qgate_b200/dist.py needs from a local runtime.  The reference has
+ * no such entry points; these few loops are this shim's own (they let the world_size-2 gloo
+ * tests drive the sharding host logic over the reference's gate / reduce / readout code). */
+
+namespace {
+
+template <class real>
+bool dataPtr(qgate::QubitStates *qs, void **ptr, int64_t *bytes) {
+    qgate_cpu::CPUQubitStates<real> *c = dynamic_cast<qgate_cpu::CPUQubitStates<real> *>(qs);
+    if (c == NULL)
+        return false;
+    *ptr = c->getPtr();
+    *bytes = (int64_t)(sizeof(real) * 2) << c->getNLanes();
+    return true;
+}
+
+bool anyDataPtr(qgb_handle h, void **ptr, int64_t *bytes) {
+    return dataPtr<double>(QS(h), ptr, bytes) || dataPtr<float>(QS(h), ptr, bytes);
+}
+
+std::map<qgb_handle, void *> g_alt;
+
+template <class real>
+void joinShard(std::complex<real> *dst, int n_dst_lanes, const qgb_handle *src, int n_src,
+               int n_product_lanes, int64_t offset) {
+    std::vector<const std::complex<real> *> ptr(n_src);
+    std::vector<int> shift(n_src), lanes(n_src);
+    int sh = 0;
+    for (int k = n_src - 1; k >= 0; --k) {
+        void *p; int64_t bytes;
+        anyDataPtr(src[k], &p, &bytes);
+        ptr[k] = static_cast<const std::complex<real> *>(p);
+        lanes[k] = QS(src[k])->getNLanes();
+        shift[k] = sh;
+        sh += lanes[k];
+    }
+    for (int64_t d = 0; d < (1LL << n_dst_lanes); ++d) {
+        int64_t i = offset + d;
+        std::complex<real> v(0, 0);
+        if (i < (1LL << n_product_lanes)) {
+            int last = n_src - 1;
+            v = ptr[last][(i >> shift[last]) & ((1LL << lanes[last]) - 1)];
+            for (int k = last - 1; k >= 0; --k)
+                v = ptr[k][(i >> shift[k]) & ((1LL << lanes[k]) - 1)] * v;
+        }
+        dst[d] = v;
+    }
+}
+
+/* cumulative array in double + upper_bound, for pools made in two steps or from a vector */
+struct ShimPool : qgate::SamplingPool {
+    std::vector<double> cum;
+    std::vector<int> empty;      /* ascending */
+    bool fp32, finalized;
+    void sample(qgate::QstateIdx *obs, int n, const double *r) {
+        for (int i = 0; i < n; ++i) {
+            double v = fp32 ? (double)(float)r[i] : r[i];
+            int64_t idx = std::upper_bound(cum.begin(), cum.end(), v) - cum.begin();
+            if (idx > (int64_t)cum.size() - 1) idx = (int64_t)cum.size() - 1;
+            for (size_t k = 0; k < empty.size(); ++k) {
+                int64_t lo = idx & ((1LL << empty[k]) - 1);
+                idx = ((idx - lo) << 1) | lo;
+            }
+            obs[i] = idx;
+        }
+    }
+};
+
+} // namespace
+
 extern "C" {
 
 const char *qgb_last_error(void) { return g_last_error.c_str(); }
@@ -150,6 +225,10 @@ int qgb_qstates_new(int prec, qgb_handle *out) {
 
 int qgb_qstates_delete(qgb_handle h) {
     QGB_TRY
+    if (g_alt.count(h)) {
+        free(g_alt[h]);
+        g_alt.erase(h);
+    }
     delete QS(h);
     QGB_CATCH
 }
@@ -369,6 +448,133 @@ int qgb_pool_delete(qgb_handle pool) {
     QGB_TRY
     delete SP(pool);
     QGB_CATCH
+}
+
+int qgb_qstates_data_ptr(qgb_handle h, uint64_t *ptr, int64_t *bytes) {
+    QGB_TRY
+    void *p; int64_t b;
+    if (!anyDataPtr(h, &p, &b))
+        return fail(QGB_ERR_RUNTIME, "not a CPU qstates.");
+    *ptr = reinterpret_cast<uint64_t>(p);
+    if (bytes) *bytes = b;
+    QGB_CATCH
+}
+
+int qgb_qstates_alt_buffer(qgb_handle h, uint64_t *ptr) {
+    QGB_TRY
+    void *p; int64_t b;
+    if (!anyDataPtr(h, &p, &b))
+        return fail(QGB_ERR_RUNTIME, "not a CPU qstates.");
+    if (!g_alt.count(h)) g_alt[h] = malloc((size_t)b);
+    *ptr = reinterpret_cast<uint64_t>(g_alt[h]);
+    QGB_CATCH
+}
+
+int qgb_qstates_flip(qgb_handle h) {
+    QGB_TRY
+    /* the reference object owns its array: exchange the contents instead of the pointers */
+    void *p; int64_t b;
+    if (!anyDataPtr(h, &p, &b) || !g_alt.count(h))
+        return fail(QGB_ERR_RUNTIME, "qstates has no spare buffer.");
+    std::vector<char> tmp((size_t)b);
+    std::memcpy(tmp.data(), p, (size_t)b);
+    std::memcpy(p, g_alt[h], (size_t)b);
+    std::memcpy(g_alt[h], tmp.data(), (size_t)b);
+    QGB_CATCH
+}
+
+int qgb_qproc_calc_norm(qgb_handle, qgb_handle h, double *norm) {
+    QGB_TRY
+    void *p; int64_t b;
+    double acc = 0.;
+    if (dataPtr<double>(QS(h), &p, &b)) {
+        const double *v = static_cast<const double *>(p);
+        for (int64_t i = 0; i < b / 8; ++i) acc += v[i] * v[i];
+    } else if (dataPtr<float>(QS(h), &p, &b)) {
+        const float *v = static_cast<const float *>(p);
+        for (int64_t i = 0; i < b / 4; ++i) acc += (double)v[i] * v[i];
+    } else
+        return fail(QGB_ERR_RUNTIME, "not a CPU qstates.");
+    *norm = acc;
+    QGB_CATCH
+}
+
+int qgb_qproc_join_shard(qgb_handle, qgb_handle dst, const qgb_handle *src, int n_src, int n_new,
+                         int n_total, int64_t offset) {
+    QGB_TRY
+    void *p; int64_t b;
+    int n_dst = QS(dst)->getNLanes();
+    if (dataPtr<double>(QS(dst), &p, &b))
+        joinShard<double>(static_cast<std::complex<double> *>(p), n_dst, src, n_src, n_total - n_new, offset);
+    else if (dataPtr<float>(QS(dst), &p, &b))
+        joinShard<float>(static_cast<std::complex<float> *>(p), n_dst, src, n_src, n_total - n_new, offset);
+    else
+        return fail(QGB_ERR_RUNTIME, "not a CPU qstates.");
+    QGB_CATCH
+}
+
+int qgb_getter_create_sampling_pool_partial(qgb_handle getter, const int *lane_tables, const int *n_per,
+                                            const qgb_handle *qstates_list, int n_qstates, int n_lanes,
+                                            int n_hidden, qgb_handle *pool, double *local_total) {
+    QGB_TRY
+    bool fp64 = dynamic_cast<qgate_cpu::CPUQubitsStatesGetter<double> *>(QG(getter)) != NULL;
+    ShimPool *sp = new ShimPool();
+    sp->fp32 = !fp64;
+    sp->finalized = false;
+    int64_t n = 1LL << n_lanes;
+    sp->cum.resize((size_t)n);
+    if (fp64) {
+        QG(getter)->prepareProbArray(sp->cum.data(), toTables(lane_tables, n_per, n_qstates),
+                                     toList(qstates_list, n_qstates), n_lanes, n_hidden);
+    } else {
+        std::vector<float> tmp((size_t)n);
+        QG(getter)->prepareProbArray(tmp.data(), toTables(lane_tables, n_per, n_qstates),
+                                     toList(qstates_list, n_qstates), n_lanes, n_hidden);
+        for (int64_t i = 0; i < n; ++i) sp->cum[i] = tmp[i];
+    }
+    double acc = 0.;
+    for (int64_t i = 0; i < n; ++i) { acc += sp->cum[i]; sp->cum[i] = acc; }
+    *local_total = acc;
+    *pool = reinterpret_cast<qgb_handle>(static_cast<qgate::SamplingPool *>(sp));
+    QGB_CATCH
+}
+
+int qgb_pool_finalize(qgb_handle pool, double offset, double total) {
+    QGB_TRY
+    ShimPool *sp = dynamic_cast<ShimPool *>(SP(pool));
+    if (sp == NULL || sp->finalized)
+        return fail(QGB_ERR_RUNTIME, "sampling pool is already finalized.");
+    double norm = 1. / total;
+    for (size_t i = 0; i < sp->cum.size(); ++i) sp->cum[i] = (offset + sp->cum[i]) * norm;
+    sp->finalized = true;
+    QGB_CATCH
+}
+
+int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes, const int *empty_lanes,
+                             int n_empty, qgb_handle *pool) {
+    QGB_TRY
+    ShimPool *sp = new ShimPool();
+    sp->fp32 = prec == QGB_PREC_FP32;
+    sp->cum.assign(prob, prob + (1LL << n_lanes));
+    double acc = 0.;
+    for (size_t i = 0; i < sp->cum.size(); ++i) { acc += sp->cum[i]; sp->cum[i] = acc; }
+    if (!(std::fabs(acc - 1.) <= 0.05)) {
+        delete sp;
+        return fail(QGB_ERR_RUNTIME, "error in probability sum is beyond 0.05.");
+    }
+    for (size_t i = 0; i < sp->cum.size(); ++i) sp->cum[i] *= 1. / acc;
+    sp->empty.assign(empty_lanes, empty_lanes + n_empty);
+    std::sort(sp->empty.begin(), sp->empty.end());
+    sp->finalized = true;
+    *pool = reinterpret_cast<qgb_handle>(static_cast<qgate::SamplingPool *>(sp));
+    QGB_CATCH
+}
+
+int qgb_qstates_ipc_export(qgb_handle, void *, int64_t *) { return fail(QGB_ERR_RUNTIME, "no CUDA IPC in the CPU shim."); }
+int qgb_ipc_open(const void *, uint64_t *) { return fail(QGB_ERR_RUNTIME, "no CUDA IPC in the CPU shim."); }
+int qgb_ipc_close(uint64_t) { return fail(QGB_ERR_RUNTIME, "no CUDA IPC in the CPU shim."); }
+int qgb_qstates_exchange_p2p(qgb_handle, const uint64_t *, int, const int *, int) {
+    return fail(QGB_ERR_RUNTIME, "no peer-memory exchange in the CPU shim.");
 }
 
 int qgb_stats_get(qgb_stats *out) { *out = g_stats; return QGB_OK; }

@@ -79,6 +79,19 @@ SIGNATURES = {
     'qgb_stats_reset': [],
     'qgb_qproc_flush': [_h, _h],
     'qgb_set_option': [C.c_char_p, _i64],
+    # sharding support
+    'qgb_qstates_data_ptr': [_h, _hp, _i64p],
+    'qgb_qstates_alt_buffer': [_h, _hp],
+    'qgb_qstates_flip': [_h],
+    'qgb_qproc_calc_norm': [_h, _h, _dp],
+    'qgb_qproc_join_shard': [_h, _h, _hp, _i, _i, _i, _i64],
+    'qgb_getter_create_sampling_pool_partial': [_h, _ip, _ip, _hp, _i, _i, _i, _hp, _dp],
+    'qgb_pool_finalize': [_h, _d, _d],
+    'qgb_pool_from_prob_array': [_i, _dp, _i, _ip, _i, _hp],
+    'qgb_qstates_ipc_export': [_h, _p, _i64p],
+    'qgb_ipc_open': [_p, _hp],
+    'qgb_ipc_close': [C.c_uint64],
+    'qgb_qstates_exchange_p2p': [_h, _hp, _i, _ip, _i],
 }
 _NON_STATUS = {
     'qgb_last_error': ([], C.c_char_p),

@@ -1,0 +1,100 @@
+/*
+ * dist.cu — lane exchange between shards over NVLink peer memory (sm_100a).
+ *
+ * A state vector sharded on its g high-order (global) lanes keeps one shard of 2^(n-g)
+ * amplitudes per GPU (one process each).  A non-diagonal gate on a global lane needs that
+ * lane to become local: k global lanes trade places with k local "victim" lanes.  Seen from
+ * rank R whose k selected global bits are s: the amplitude with local index i whose victim
+ * bits are j != s belongs, after the exchange, to the rank whose selected bits are j, at the
+ * local index i' = i with the victim bits replaced by s — and that rank's amplitude at i'
+ * belongs here at i.  So the exchange is a set of pairwise in-place swaps between this shard
+ * and 2^k - 1 peers.  This kernel does them directly through peer pointers (CUDA IPC mappings
+ * of the other ranks' shards), 16 bytes per access: no staging buffer, no second copy, both
+ * directions of every NVLink used at once (each rank performs half of the swaps of each pair:
+ * it pulls the peer's value over the link and pushes its own).
+ *
+ * What it replaces in the reference: there is no exchange step — every gate on a high lane
+ * streams half of every chunk over the link through fine-grained peer loads/stores inside
+ * the gate kernel (MultiChunkPtr.h:30-41, ProcessorRelocator.cpp:51-73), every time.
+ */
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace qgb {
+
+namespace {
+
+__device__ __forceinline__ uint64_t insert_bit(uint64_t idx, int pos, uint64_t bit) {
+    const uint64_t lo = idx & ((1ull << pos) - 1ull);
+    return ((idx - lo) << 1) | (bit << pos) | lo;
+}
+
+/* One work item = one 16-byte unit of this shard that has to trade places.  Items are
+ * numbered t = jj * 2^(n_unit_bits - k - 1) + rest, where jj enumerates the 2^k - 1 peers and
+ * `rest` the unit index with the victim bits and the split bit taken out. */
+__global__ void __launch_bounds__(256)
+exchange_p2p_kernel(uint4 *__restrict__ local, const __grid_constant__ ExchangeParams ep) {
+    const int k = ep.k, s = ep.my_sel;
+    const int rest_bits = ep.n_unit_bits - k - 1;
+    const uint64_t n_rest = 1ull << rest_bits;
+    const uint64_t n_items = n_rest * ((1ull << k) - 1ull);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    /* positions to re-insert, ascending: the k victims and the split bit */
+    int pos[QGB_MAX_EXCHANGE_LANES + 1];
+    int which[QGB_MAX_EXCHANGE_LANES + 1]; /* victim number, or -1 for the split bit */
+    {
+        int n = 0, v = 0;
+        bool split_done = false;
+        while (n < k + 1) {
+            if (!split_done && (v >= k || ep.split < ep.victim[v])) {
+                pos[n] = ep.split;
+                which[n] = -1;
+                split_done = true;
+            } else {
+                pos[n] = ep.victim[v];
+                which[n] = v;
+                ++v;
+            }
+            ++n;
+        }
+    }
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
+        const uint64_t rest = t & (n_rest - 1ull);
+        int j = (int)(t >> rest_bits);
+        if (j >= s) ++j; /* skip my own block */
+        /* the lower-numbered rank of a pair moves the units whose split bit is 0 */
+        const uint64_t split_bit = (s < j) ? 0ull : 1ull;
+        uint64_t mine = rest, theirs = rest;
+#pragma unroll
+        for (int n = 0; n < QGB_MAX_EXCHANGE_LANES + 1; ++n) {
+            if (n < k + 1) {
+                const int w = which[n];
+                const uint64_t bm = (w < 0) ? split_bit : (uint64_t)((j >> w) & 1);
+                const uint64_t bt = (w < 0) ? split_bit : (uint64_t)((s >> w) & 1);
+                mine = insert_bit(mine, pos[n], bm);
+                theirs = insert_bit(theirs, pos[n], bt);
+            }
+        }
+        uint4 *remote = reinterpret_cast<uint4 *>(ep.peer[j]);
+        const uint4 a = local[mine];
+        const uint4 b = remote[theirs];
+        local[mine] = b;
+        remote[theirs] = a;
+    }
+}
+
+} // namespace
+
+cudaError_t launch_exchange_p2p(void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream) {
+    const int rest_bits = ep.n_unit_bits - ep.k - 1;
+    const uint64_t n_items = (1ull << rest_bits) * ((1ull << ep.k) - 1ull);
+    uint64_t blocks = (n_items + 255) / 256;
+    const uint64_t cap = (uint64_t)(sm_count > 0 ? sm_count : 148) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    exchange_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<uint4 *>(local), ep);
+    return cudaGetLastError();
+}
+
+} // namespace qgb

@@ -169,6 +169,7 @@ struct QStates {
     int prec;
     int n_lanes = -1;
     void *d_amp = nullptr;
+    void *d_alt = nullptr; /* spare array for out-of-place exchanges (sharded states only) */
     std::vector<Gate> queue;
     size_t elem() const { return prec == QGB_PREC_FP64 ? 16 : 8; }
     size_t bytes() const { return elem() << n_lanes; }
@@ -186,6 +187,8 @@ struct Pool {
     int prec;
     int n_lanes;
     double *d_cum = nullptr;
+    double *d_sums = nullptr; /* block sums + total, kept between `partial` and `finalize` */
+    bool finalized = false;
     SortedBits empty;
 };
 
@@ -274,11 +277,21 @@ void flush_tiled(QStates *qs) {
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
-    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1) > (size_t)g.max_smem_optin) --cfg.T;
+    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
     if (cfg.T >= qs->n_lanes) cfg.L = std::min((int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64), cfg.T);
     cfg.max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, QGB_MAX_OPS));
+    {
+        /* stages: each costs a per-thread table entry in shared memory; keep the CTA small enough
+         * for the occupancy its launch bounds ask for (3 / 2 / 1 CTAs per SM) */
+        const int nthr = 1 << (cfg.T - cfg.K);
+        const int want_ctas = nthr <= 256 ? 3 : (nthr <= 512 ? 2 : 1);
+        const size_t budget = (size_t)g.max_smem_optin / want_ctas - 1024;
+        int ms = QGB_MAX_STAGES;
+        while (ms > 2 && tile_pass_smem_bytes(qs->prec, cfg.T, cfg.L, ms) > budget) --ms;
+        cfg.max_stages = ms;
+    }
     cfg.max_cost = (int)g.opt.max_cost;
     cfg.lookahead = (int)g.opt.lookahead;
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
@@ -337,6 +350,10 @@ void free_qstates_buffer(QStates *qs) {
     if (qs->d_amp) {
         g.pool.release(qs->d_amp);
         qs->d_amp = nullptr;
+    }
+    if (qs->d_alt) {
+        g.pool.release(qs->d_alt);
+        qs->d_alt = nullptr;
     }
     qs->queue.clear();
 }
@@ -445,7 +462,7 @@ int qgb_devices_initialize(const int *device_ids, int n_device_ids, int max_po2i
     CUDA_CHECK(cudaDeviceGetAttribute(&g.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    CUDA_CHECK(tile_pass_configure(g.max_smem_optin));
+    CUDA_CHECK(tile_pass_configure(g.max_smem_optin, g.sm_count));
     g.pool.budget = memory_store_size;
     CUDA_CHECK(cudaMalloc(&g.d_partials, sizeof(double) * 4096));
     CUDA_CHECK(cudaMallocHost(&g.h_scalar, sizeof(double) * 16));
@@ -464,10 +481,11 @@ int qgb_devices_clear(void) {
     cudaStreamSynchronize(g.stream);
     for (QStates *qs : g.qstates) {
         qs->d_amp = nullptr;
+        qs->d_alt = nullptr;
         qs->queue.clear();
         qs->n_lanes = -1;
     }
-    for (Pool *p : g.pools) p->d_cum = nullptr;
+    for (Pool *p : g.pools) p->d_cum = p->d_sums = nullptr;
     g.pool.clear();
     cudaFree(g.d_partials);
     cudaFreeHost(g.h_scalar);
@@ -617,8 +635,8 @@ int qgb_qproc_calc_probability(qgb_handle qp, qgb_handle h, int lane, double *pr
     QGB_CATCH
 }
 
-int qgb_qproc_join(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes) {
-    QGB_TRY
+static void join_impl(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes,
+                      int n_total_lanes, int64_t index_offset) {
     QP(qp);
     require_init();
     QStates *dst = QS(hdst);
@@ -638,11 +656,142 @@ int qgb_qproc_join(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, i
         jp.shift[k] = shift;
         shift += src->n_lanes;
     }
-    if (n_new_lanes < 0 || shift + n_new_lanes != dst->n_lanes)
+    if (n_total_lanes < 0) n_total_lanes = dst->n_lanes;
+    if (n_new_lanes < 0 || shift + n_new_lanes != n_total_lanes || dst->n_lanes > n_total_lanes)
         fail(QGB_ERR_INVALID, "join: %d source lanes + %d new lanes != %d destination lanes.", shift,
-             n_new_lanes, dst->n_lanes);
+             n_new_lanes, n_total_lanes);
+    if (index_offset < 0 || (index_offset & (((int64_t)1 << dst->n_lanes) - 1)) != 0 ||
+        index_offset >= ((int64_t)1 << n_total_lanes))
+        fail(QGB_ERR_INVALID, "join: bad shard offset.");
     dst->queue.clear();
-    CUDA_CHECK(launch_join(dst->prec, dst->d_amp, dst->n_lanes, shift, jp, g.stream));
+    CUDA_CHECK(launch_join(dst->prec, dst->d_amp, dst->n_lanes, shift, (uint64_t)index_offset, jp, g.stream));
+    g.stats.kernel_launches += 1;
+}
+
+int qgb_qproc_join(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes) {
+    QGB_TRY
+    join_impl(qp, hdst, src_list, n_src, n_new_lanes, -1, 0);
+    QGB_CATCH
+}
+
+int qgb_qproc_join_shard(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes,
+                         int n_total_lanes, int64_t index_offset) {
+    QGB_TRY
+    join_impl(qp, hdst, src_list, n_src, n_new_lanes, n_total_lanes, index_offset);
+    QGB_CATCH
+}
+
+int qgb_qproc_calc_norm(qgb_handle qp, qgb_handle h, double *norm) {
+    QGB_TRY
+    QP(qp);
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    flush(qs);
+    CUDA_CHECK(launch_norm(qs->prec, qs->d_amp, qs->n_lanes, g.d_partials, g.d_partials + 2048, g.stream));
+    g.stats.kernel_launches += 2;
+    CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, g.d_partials + 2048, sizeof(double), cudaMemcpyDeviceToHost,
+                               g.stream));
+    stream_sync();
+    g.stats.d2h_bytes += sizeof(double);
+    *norm = g.h_scalar[0];
+    QGB_CATCH
+}
+
+int qgb_qstates_data_ptr(qgb_handle h, uint64_t *ptr, int64_t *bytes) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    flush(qs);
+    *ptr = reinterpret_cast<uint64_t>(qs->d_amp);
+    if (bytes) *bytes = (int64_t)qs->bytes();
+    QGB_CATCH
+}
+
+int qgb_qstates_alt_buffer(qgb_handle h, uint64_t *ptr) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (!qs->d_alt) qs->d_alt = g.pool.alloc(qs->bytes());
+    *ptr = reinterpret_cast<uint64_t>(qs->d_alt);
+    QGB_CATCH
+}
+
+int qgb_qstates_flip(qgb_handle h) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (!qs->d_alt) fail(QGB_ERR_RUNTIME, "qstates has no spare buffer.");
+    flush(qs);
+    std::swap(qs->d_amp, qs->d_alt);
+    QGB_CATCH
+}
+
+int qgb_qstates_ipc_export(qgb_handle h, void *handle64, int64_t *offset) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    CUDA_CHECK(cudaIpcGetMemHandle(&hd, qs->d_amp)); /* every pool block is its own cudaMalloc */
+    std::memcpy(handle64, &hd, sizeof(hd));
+    if (offset) *offset = 0;
+    QGB_CATCH
+}
+
+int qgb_ipc_open(const void *handle64, uint64_t *base_ptr) {
+    QGB_TRY
+    require_init();
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, sizeof(hd));
+    void *p = nullptr;
+    CUDA_CHECK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    *base_ptr = reinterpret_cast<uint64_t>(p);
+    QGB_CATCH
+}
+
+int qgb_ipc_close(uint64_t base_ptr) {
+    QGB_TRY
+    require_init();
+    CUDA_CHECK(cudaIpcCloseMemHandle(reinterpret_cast<void *>(base_ptr)));
+    QGB_CATCH
+}
+
+int qgb_qstates_exchange_p2p(qgb_handle h, const uint64_t *peer_ptrs, int k, const int *victim_lanes,
+                             int my_sel) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (k < 1 || k > QGB_MAX_EXCHANGE_LANES) fail(QGB_ERR_INVALID, "exchange of %d lanes is not supported.", k);
+    if (my_sel < 0 || my_sel >= (1 << k)) fail(QGB_ERR_INVALID, "bad exchange selector.");
+    const int unit_shift = qs->prec == QGB_PREC_FP64 ? 0 : 1; /* 16-byte units */
+    ExchangeParams ep;
+    ep.k = k;
+    ep.my_sel = my_sel;
+    ep.n_unit_bits = qs->n_lanes - unit_shift;
+    uint64_t vmask = 0;
+    for (int i = 0; i < k; ++i) {
+        check_lane(qs, victim_lanes[i]);
+        if (victim_lanes[i] < unit_shift || (i > 0 && victim_lanes[i] <= victim_lanes[i - 1]))
+            fail(QGB_ERR_INVALID, "victim lanes must ascend and lie above the 16-byte unit.");
+        ep.victim[i] = victim_lanes[i] - unit_shift;
+        vmask |= 1ull << ep.victim[i];
+    }
+    if (ep.n_unit_bits < k + 1) fail(QGB_ERR_INVALID, "state too small for a %d-lane exchange.", k);
+    ep.split = -1; /* highest unit bit that is not a victim: halves the work of every rank pair */
+    for (int b = ep.n_unit_bits - 1; b >= 0; --b)
+        if (!(vmask & (1ull << b))) {
+            ep.split = b;
+            break;
+        }
+    for (int j = 0; j < (1 << k); ++j) ep.peer[j] = reinterpret_cast<void *>(peer_ptrs[j]);
+    flush(qs);
+    CUDA_CHECK(launch_exchange_p2p(qs->d_amp, ep, g.sm_count, g.stream));
     g.stats.kernel_launches += 1;
     QGB_CATCH
 }
@@ -842,38 +991,35 @@ int qgb_getter_prepare_prob_array(qgb_handle getter, void *prob, const int *lane
     QGB_CATCH
 }
 
-int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, const int *n_per,
-                                    const qgb_handle *qstates_list, int n_qstates, int n_lanes, int n_hidden,
-                                    const int *empty_lanes, int n_empty, qgb_handle *out) {
-    QGB_TRY
-    Getter *gt = QG(getter);
-    require_init();
-    if (n_empty < 0 || n_empty > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of empty lanes.");
-    double *d_prob = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes,
-                                       n_hidden);
-    const int64_t n = (int64_t)1 << n_lanes;
+/* scan phases 1+2 over d_prob (2^n_lanes doubles): leaves the block sums in pool->d_sums and
+ * returns the total (host value) */
+static double pool_scan_partial(Pool *p) {
+    const int64_t n = (int64_t)1 << p->n_lanes;
     const int64_t n_blocks = (n + 4095) / 4096;
-    double *d_sums = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)(n_blocks + 1)));
-    double *d_total = d_sums + n_blocks;
-    CUDA_CHECK(launch_scan_phase1(d_prob, n, d_sums, g.stream));
-    CUDA_CHECK(launch_scan_phase2(d_sums, n_blocks, d_total, g.stream));
+    p->d_sums = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)(n_blocks + 1)));
+    double *d_total = p->d_sums + n_blocks;
+    CUDA_CHECK(launch_scan_phase1(p->d_cum, n, p->d_sums, g.stream));
+    CUDA_CHECK(launch_scan_phase2(p->d_sums, n_blocks, d_total, g.stream));
     CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, d_total, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
     stream_sync();
     g.stats.kernel_launches += 2;
-    const double total = g.h_scalar[0];
-    /* CPUSamplingPool.cpp:31-34 */
-    if (!(std::fabs(total - 1.) <= 0.05)) {
-        g.pool.release(d_sums);
-        g.pool.release(d_prob);
-        fail(QGB_ERR_RUNTIME, "error in probability sum is beyond 0.05., %g.", total);
-    }
-    CUDA_CHECK(launch_scan_phase3(d_prob, n, d_sums, d_total, g.stream));
+    g.stats.d2h_bytes += sizeof(double);
+    return g.h_scalar[0];
+}
+
+/* phase 3: cum[i] = (offset + scan[i]) * (1 / total) */
+static void pool_scan_finalize(Pool *p, double offset, double total) {
+    if (p->finalized || !p->d_sums) fail(QGB_ERR_RUNTIME, "sampling pool is already finalized.");
+    const int64_t n = (int64_t)1 << p->n_lanes;
+    CUDA_CHECK(launch_scan_phase3(p->d_cum, n, p->d_sums, offset, 1. / total, g.stream));
     g.stats.kernel_launches += 1;
-    g.pool.release(d_sums); /* stream-ordered: reused only by later work on the same stream */
-    Pool *p = new Pool();
-    p->prec = gt->prec;
-    p->n_lanes = n_lanes;
-    p->d_cum = d_prob;
+    g.pool.release(p->d_sums); /* stream-ordered: reused only by later work on the same stream */
+    p->d_sums = nullptr;
+    p->finalized = true;
+}
+
+static void pool_set_empty_lanes(Pool *p, const int *empty_lanes, int n_empty) {
+    if (n_empty < 0 || n_empty > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of empty lanes.");
     std::vector<int> sorted(empty_lanes, empty_lanes + n_empty);
     std::sort(sorted.begin(), sorted.end());
     p->empty.n = 0;
@@ -881,7 +1027,104 @@ int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, c
         if (v < 0 || v >= 63) fail(QGB_ERR_INVALID, "bad empty lane %d.", v);
         p->empty.pos[p->empty.n++] = (int8_t)v;
     }
+}
+
+static void pool_destroy(Pool *p) {
+    if (p->d_cum) g.pool.release(p->d_cum);
+    if (p->d_sums) g.pool.release(p->d_sums);
+    g.pools.erase(p);
+    delete p;
+}
+
+/* CPUSamplingPool.cpp:31-34 */
+static void pool_check_total(Pool *p, double total) {
+    if (!(std::fabs(total - 1.) <= 0.05)) {
+        pool_destroy(p);
+        fail(QGB_ERR_RUNTIME, "error in probability sum is beyond 0.05., %g.", total);
+    }
+}
+
+int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, const int *n_per,
+                                    const qgb_handle *qstates_list, int n_qstates, int n_lanes, int n_hidden,
+                                    const int *empty_lanes, int n_empty, qgb_handle *out) {
+    QGB_TRY
+    Getter *gt = QG(getter);
+    require_init();
+    if (n_empty < 0 || n_empty > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of empty lanes.");
+    Pool *p = new Pool();
+    p->prec = gt->prec;
+    p->n_lanes = n_lanes;
+    p->empty.n = 0;
     g.pools.insert(p);
+    try {
+        p->d_cum = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
+        pool_set_empty_lanes(p, empty_lanes, n_empty);
+    } catch (...) {
+        pool_destroy(p);
+        throw;
+    }
+    const double total = pool_scan_partial(p);
+    pool_check_total(p, total);
+    pool_scan_finalize(p, 0., total);
+    *out = reinterpret_cast<qgb_handle>(p);
+    QGB_CATCH
+}
+
+int qgb_getter_create_sampling_pool_partial(qgb_handle getter, const int *lane_tables, const int *n_per,
+                                            const qgb_handle *qstates_list, int n_qstates, int n_lanes,
+                                            int n_hidden, qgb_handle *out, double *local_total) {
+    QGB_TRY
+    Getter *gt = QG(getter);
+    require_init();
+    Pool *p = new Pool();
+    p->prec = gt->prec;
+    p->n_lanes = n_lanes;
+    p->empty.n = 0;
+    g.pools.insert(p);
+    try {
+        p->d_cum = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
+    } catch (...) {
+        pool_destroy(p);
+        throw;
+    }
+    *local_total = pool_scan_partial(p);
+    *out = reinterpret_cast<qgb_handle>(p);
+    QGB_CATCH
+}
+
+int qgb_pool_finalize(qgb_handle pool, double offset, double total) {
+    QGB_TRY
+    Pool *p = SP(pool);
+    require_init();
+    if (!(total > 0.)) fail(QGB_ERR_INVALID, "total probability must be positive.");
+    pool_scan_finalize(p, offset, total);
+    QGB_CATCH
+}
+
+int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes, const int *empty_lanes, int n_empty,
+                             qgb_handle *out) {
+    QGB_TRY
+    check_prec(prec);
+    require_init();
+    if (n_lanes < 0 || n_lanes > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad lane count %d.", n_lanes);
+    Pool *p = new Pool();
+    p->prec = prec;
+    p->n_lanes = n_lanes;
+    p->empty.n = 0;
+    g.pools.insert(p);
+    try {
+        const size_t bytes = sizeof(double) << n_lanes;
+        p->d_cum = static_cast<double *>(g.pool.alloc(bytes));
+        CUDA_CHECK(cudaMemcpyAsync(p->d_cum, prob, bytes, cudaMemcpyHostToDevice, g.stream));
+        g.stats.h2d_bytes += (int64_t)bytes;
+        pool_set_empty_lanes(p, empty_lanes, n_empty);
+    } catch (...) {
+        pool_destroy(p);
+        throw;
+    }
+    const double total = pool_scan_partial(p);
+    pool_check_total(p, total);
+    pool_scan_finalize(p, 0., total);
     *out = reinterpret_cast<qgb_handle>(p);
     QGB_CATCH
 }
@@ -893,6 +1136,7 @@ int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *
     Pool *p = SP(pool);
     require_init();
     if (!p->d_cum) fail(QGB_ERR_RUNTIME, "sampling pool was released.");
+    if (!p->finalized) fail(QGB_ERR_RUNTIME, "sampling pool is not finalized.");
     if (n_samples < 0) fail(QGB_ERR_INVALID, "negative number of samples.");
     if (n_samples == 0) return QGB_OK;
     const size_t n = (size_t)n_samples;
@@ -912,10 +1156,7 @@ int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *
 
 int qgb_pool_delete(qgb_handle pool) {
     QGB_TRY
-    Pool *p = SP(pool);
-    if (p->d_cum) g.pool.release(p->d_cum);
-    g.pools.erase(p);
-    delete p;
+    pool_destroy(SP(pool));
     QGB_CATCH
 }
 

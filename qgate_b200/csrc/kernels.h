@@ -35,9 +35,9 @@ struct GatherParams {
 /* ---- gates ----------------------------------------------------------------------- */
 template <typename real>
 cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, cudaStream_t stream);
-/* smem bytes the tile kernel needs for (T, L) */
-size_t tile_pass_smem_bytes(int prec, int T, int L);
-cudaError_t tile_pass_configure(int max_smem_optin);
+/* smem bytes the tile kernel needs for (T, L) and n_stages stages */
+size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages);
+cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
                                uint64_t ctrl_mask, cudaStream_t stream);
@@ -48,6 +48,9 @@ cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_
 /* partial sums -> *d_result (double) = sum_{bit lane == 0} |a|^2; d_partials holds >= 2048 doubles */
 cudaError_t launch_prob0(int prec, const void *amp, int n_lanes, int lane, double *d_partials,
                          double *d_result, cudaStream_t stream);
+/* *d_result = sum of |a|^2 over the whole array */
+cudaError_t launch_norm(int prec, const void *amp, int n_lanes, double *d_partials, double *d_result,
+                        cudaStream_t stream);
 cudaError_t launch_decohere(int prec, void *amp, int n_lanes, int lane, int value, double norm,
                             cudaStream_t stream);
 cudaError_t launch_decohere_separate(int prec, void *dst, const void *src, int n_src_lanes, int lane,
@@ -60,9 +63,10 @@ struct JoinParams {
     int32_t shift[QGB_MAX_QSTATES];
     int32_t n_lanes[QGB_MAX_QSTATES];
 };
-/* dst[i] = prod_k src_k[(i >> shift_k) & mask_k] for i < 2^n_product, 0 above */
+/* dst[d] = prod_k src_k[(i >> shift_k) & mask_k] for i = index_offset + d < 2^n_product, 0 above
+ * (index_offset != 0: dst is one shard of the product) */
 cudaError_t launch_join(int prec, void *dst, int n_dst_lanes, int n_product_lanes,
-                        const JoinParams &jp, cudaStream_t stream);
+                        uint64_t index_offset, const JoinParams &jp, cudaStream_t stream);
 
 /* ---- readout ------------------------------------------------------------------------ */
 /* out[j] (complex<real> for mathop 0, real for mathop 1), j in [0, count):
@@ -86,12 +90,25 @@ cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, i
  * d_block_sums holds ceil(n / 4096) doubles; *d_total receives the grand total. */
 cudaError_t launch_scan_phase1(const double *d_prob, int64_t n, double *d_block_sums, cudaStream_t stream);
 cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d_total, cudaStream_t stream);
-/* cum[i] = (offset_block + inclusive_scan_in_block) * norm, norm = 1 / total read from *d_total */
+/* cum[i] = (global_offset + offset_block + inclusive_scan_in_block) * norm */
 cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums,
-                               const double *d_total, cudaStream_t stream);
+                               double global_offset, double norm, cudaStream_t stream);
 /* obs[i] = deposit(upper_bound(cum, r_i), perm); r is cast to float first when prec is FP32
  * (CPUSamplingPool.cpp:74) */
 cudaError_t launch_sample(int prec, const double *d_cum, int n_lanes, const double *d_rand,
                           int64_t *d_obs, int n_samples, SortedBits empty_lanes, cudaStream_t stream);
+
+/* ---- sharded states: lane exchange over peer memory (dist.cu) --------------------------- */
+#define QGB_MAX_EXCHANGE_LANES 4
+
+struct ExchangeParams {
+    int32_t k;                 /* lanes exchanged at once                                        */
+    int32_t my_sel;            /* this rank's value of the k selected global bits               */
+    int32_t n_unit_bits;       /* log2 of the shard size in 16-byte units                        */
+    int32_t split;             /* unit bit that decides which rank of a pair moves an element   */
+    int32_t victim[QGB_MAX_EXCHANGE_LANES]; /* ascending unit-bit positions of the local lanes */
+    void *peer[1 << QGB_MAX_EXCHANGE_LANES]; /* peer[j]: shard of the rank whose bits equal j   */
+};
+cudaError_t launch_exchange_p2p(void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream);
 
 } // namespace qgb

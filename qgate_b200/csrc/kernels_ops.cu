@@ -163,10 +163,11 @@ apply_reset_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_half,
 template <typename real>
 __global__ void __launch_bounds__(256)
 join_kernel(typename Cplx<real>::type *__restrict__ dst, uint64_t n_dst, uint64_t n_product,
-            const __grid_constant__ JoinParams jp) {
+            uint64_t index_offset, const __grid_constant__ JoinParams jp) {
     typedef typename Cplx<real>::type cplx;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_dst; i += stride) {
+    for (uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; d < n_dst; d += stride) {
+        const uint64_t i = index_offset + d; /* index in the whole product (shards: offset != 0) */
         cplx v;
         if (i < n_product) {
             const int last = jp.n_src - 1;
@@ -182,7 +183,7 @@ join_kernel(typename Cplx<real>::type *__restrict__ dst, uint64_t n_dst, uint64_
             v.x = (real)0;
             v.y = (real)0;
         }
-        dst[i] = v;
+        dst[d] = v;
     }
 }
 
@@ -323,7 +324,7 @@ scan_phase2_kernel(double *__restrict__ block_sums, int64_t n_blocks, double *__
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_phase3_kernel(double *__restrict__ prob, int64_t n, const double *__restrict__ block_sums,
-                   const double *__restrict__ total) {
+                   double global_offset, double norm) {
     const int64_t begin = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
     double v[SCAN_PER_THREAD];
     double acc = 0.;
@@ -344,8 +345,9 @@ scan_phase3_kernel(double *__restrict__ prob, int64_t n, const double *__restric
         }
     }
     __syncthreads();
-    const double offset = block_sums[blockIdx.x] + tsum[threadIdx.x];
-    const double norm = 1. / *total; /* CPUSamplingPool.cpp:36: norm = 1 / sum, then cum *= norm */
+    /* global_offset: total of the lower ranks' shards (0 on one GPU, which keeps the sum exact);
+     * norm = 1 / sum, then cum *= norm (CPUSamplingPool.cpp:36) */
+    const double offset = global_offset + (block_sums[blockIdx.x] + tsum[threadIdx.x]);
 #pragma unroll
     for (int u = 0; u < SCAN_PER_THREAD; ++u)
         if (begin + u < n) prob[begin + u] = (offset + v[u]) * norm;
@@ -413,6 +415,23 @@ cudaError_t launch_prob0(int prec, const void *amp, int n_lanes, int lane, doubl
     return cudaGetLastError();
 }
 
+cudaError_t launch_norm(int prec, const void *amp, int n_lanes, double *d_partials, double *d_result,
+                        cudaStream_t stream) {
+    /* prob0_kernel with a "lane" above every index bit sums |a|^2 over the whole array */
+    const uint64_t n = 1ull << n_lanes;
+    const unsigned nblocks = grid_for((n + 3) / 4, 256, 148 * 8);
+    if (prec == 1)
+        prob0_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<const double2 *>(amp), n, 62,
+                                                         d_partials);
+    else
+        prob0_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<const float2 *>(amp), n, 62,
+                                                        d_partials);
+    cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) return rc;
+    final_sum_kernel<<<1, 1024, 0, stream>>>(d_partials, (int)nblocks, d_result);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decohere(int prec, void *amp, int n_lanes, int lane, int value, double norm,
                             cudaStream_t stream) {
     const uint64_t n = 1ull << n_lanes;
@@ -453,16 +472,16 @@ cudaError_t launch_apply_reset(int prec, void *amp, int n_lanes, int lane, cudaS
     return cudaGetLastError();
 }
 
-cudaError_t launch_join(int prec, void *dst, int n_dst_lanes, int n_product_lanes, const JoinParams &jp,
-                        cudaStream_t stream) {
+cudaError_t launch_join(int prec, void *dst, int n_dst_lanes, int n_product_lanes, uint64_t index_offset,
+                        const JoinParams &jp, cudaStream_t stream) {
     const uint64_t n_dst = 1ull << n_dst_lanes, n_product = 1ull << n_product_lanes;
     const unsigned nblocks = grid_for(n_dst, 256, kStreamCap);
     if (prec == 1)
         join_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double2 *>(dst), n_dst,
-                                                        n_product, jp);
+                                                        n_product, index_offset, jp);
     else
         join_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float2 *>(dst), n_dst, n_product,
-                                                       jp);
+                                                       index_offset, jp);
     return cudaGetLastError();
 }
 
@@ -528,10 +547,10 @@ cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums, const double *d_total,
-                               cudaStream_t stream) {
+cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums, double global_offset,
+                               double norm, cudaStream_t stream) {
     const unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    scan_phase3_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums, d_total);
+    scan_phase3_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums, global_offset, norm);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,9 @@
 
 #include "kernels.h"
 
+#define QGB_K64 3
+#define QGB_K32 4
+
 namespace qgb {
 
 namespace {
@@ -30,9 +33,18 @@ template <typename real> struct Cplx;
 template <> struct Cplx<float> { typedef float2 type; };
 template <> struct Cplx<double> { typedef double2 type; };
 
-template <typename real> __device__ __forceinline__ uint32_t swz(uint32_t e);
-template <> __device__ __forceinline__ uint32_t swz<double>(uint32_t e) { return e ^ ((e >> 3) & 7u); }
-template <> __device__ __forceinline__ uint32_t swz<float>(uint32_t e) { return e ^ (((e >> 4) & 7u) << 1); }
+template <typename real> __device__ __forceinline__ uint32_t swz(uint32_t e) {
+    return tile_swizzle(e, sizeof(real) == 4);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 template <int K> __device__ __forceinline__ uint32_t reg_offset(int r, const uint32_t (&rb)[K]) {
     uint32_t off = 0;
@@ -49,16 +61,16 @@ template <int K> __device__ __forceinline__ uint32_t reg_offset(int r, const uin
  * with per-amplitude divergent predicates ptxas copied the whole register file (32 MOVs)
  * on every op (profiles/r1a_tile_f64_summary.md). */
 
-template <typename real, int K, int J>
-__device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K], const real *m,
-                                          uint32_t regmask) {
+template <typename real, int K, int J, bool ALL>
+__device__ __forceinline__ void apply_gen_pairs(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                                uint32_t regmask) {
     const real m00r = m[0], m00i = m[1], m01r = m[2], m01i = m[3];
     const real m10r = m[4], m10i = m[5], m11r = m[6], m11i = m[7];
 #pragma unroll
     for (int r0 = 0; r0 < (1 << K); ++r0) {
         if (r0 & (1 << J)) continue;
         const int r1 = r0 | (1 << J);
-        if (regmask & (1u << r0)) {
+        if (ALL || (regmask & (1u << r0))) {
             const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
             a[r0].x = m00r * q0r - m00i * q0i + m01r * q1r - m01i * q1i;
             a[r0].y = m00r * q0i + m00i * q0r + m01r * q1i + m01i * q1r;
@@ -66,6 +78,17 @@ __device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K]
             a[r1].y = m10r * q0i + m10i * q0r + m11r * q1i + m11i * q1r;
         }
     }
+}
+
+/* 2x2 on register bit J.  No register-bit controls (regmask all ones, the usual case): one
+ * straight-line block of 2^(K-1) independent pairs for the scheduler to interleave. */
+template <typename real, int K, int J>
+__device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                          uint32_t regmask) {
+    if (regmask == (1u << (1 << K)) - 1u)
+        apply_gen_pairs<real, K, J, true>(a, m, regmask);
+    else
+        apply_gen_pairs<real, K, J, false>(a, m, regmask);
 }
 
 template <typename real, int K, int J>
@@ -110,38 +133,51 @@ __device__ __forceinline__ void apply_op(typename Cplx<real>::type (&a)[1 << K],
     if ((base & op.ctrl_out) != op.ctrl_out) return;
     const bool active = (ebase & op.cmt) == op.cmt;
     const uint32_t regmask = op.regmask;
-    const int kind = op.kind, bit = op.bit;
-    if (kind == OP_GEN) {
-        real m[8];
+    const uint32_t arm = op.arm;
+    if (arm & (ARM_GEN(0) | ARM_GEN(1) | ARM_GEN(2) | ARM_GEN(3))) {
+        if (op.cmt == 0) {
+            /* no thread-bit controls (the usual case): the matrix stays in uniform registers */
+            if (arm & ARM_GEN(0)) apply_gen<real, K, 0>(a, op.m, regmask);
+            if (K > 1 && (arm & ARM_GEN(1))) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, op.m, regmask);
+            if (K > 2 && (arm & ARM_GEN(2))) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, op.m, regmask);
+            if (K > 3 && (arm & ARM_GEN(3))) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, op.m, regmask);
+        } else {
+            real m[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m[i] = active ? op.m[i] : ((i == 0 || i == 6) ? (real)1 : (real)0);
-        if (bit == 0) apply_gen<real, K, 0>(a, m, regmask);
-        if (K > 1 && bit == 1) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, m, regmask);
-        if (K > 2 && bit == 2) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, m, regmask);
-        if (K > 3 && bit == 3) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, m, regmask);
-    } else if (kind == OP_SWAP) {
-        if (bit == 0) apply_swap<real, K, 0>(a, regmask, active);
-        if (K > 1 && bit == 1) apply_swap<real, K, (K > 1 ? 1 : 0)>(a, regmask, active);
-        if (K > 2 && bit == 2) apply_swap<real, K, (K > 2 ? 2 : 0)>(a, regmask, active);
-        if (K > 3 && bit == 3) apply_swap<real, K, (K > 3 ? 3 : 0)>(a, regmask, active);
+            for (int i = 0; i < 8; ++i) m[i] = active ? op.m[i] : ((i == 0 || i == 6) ? (real)1 : (real)0);
+            if (arm & ARM_GEN(0)) apply_gen_pairs<real, K, 0, false>(a, m, regmask);
+            if (K > 1 && (arm & ARM_GEN(1))) apply_gen_pairs<real, K, (K > 1 ? 1 : 0), false>(a, m, regmask);
+            if (K > 2 && (arm & ARM_GEN(2))) apply_gen_pairs<real, K, (K > 2 ? 2 : 0), false>(a, m, regmask);
+            if (K > 3 && (arm & ARM_GEN(3))) apply_gen_pairs<real, K, (K > 3 ? 3 : 0), false>(a, m, regmask);
+        }
+    } else if (arm & (ARM_SWAP(0) | ARM_SWAP(1) | ARM_SWAP(2) | ARM_SWAP(3))) {
+        if (arm & ARM_SWAP(0)) apply_swap<real, K, 0>(a, regmask, active);
+        if (K > 1 && (arm & ARM_SWAP(1))) apply_swap<real, K, (K > 1 ? 1 : 0)>(a, regmask, active);
+        if (K > 2 && (arm & ARM_SWAP(2))) apply_swap<real, K, (K > 2 ? 2 : 0)>(a, regmask, active);
+        if (K > 3 && (arm & ARM_SWAP(3))) apply_swap<real, K, (K > 3 ? 3 : 0)>(a, regmask, active);
     } else {
         const real d0r = active ? op.m[0] : (real)1, d0i = active ? op.m[1] : (real)0;
         const real d1r = active ? op.m[2] : (real)1, d1i = active ? op.m[3] : (real)0;
-        const uint32_t regsel = op.regsel;
-        if (regsel != 0) {
+        if (arm & ARM_DIAG_REG) {
             /* target on a register bit: d1 on the registers of regsel, d0 on the others */
+            const uint32_t regsel = op.regsel;
             apply_phase<real, K>(a, d0r, d0i, regmask & ~regsel);
             apply_phase<real, K>(a, d1r, d1i, regmask & regsel);
         } else {
             /* target on a thread bit (OP_DIAG), outside the tile (OP_DIAG_OUT), or a phase */
             bool one = (ebase & op.tsel) != 0;
-            if (kind == OP_DIAG_OUT) one = (base >> bit) & 1ull;
+            if (op.kind == OP_DIAG_OUT) one = (base >> op.bit) & 1ull;
             apply_phase<real, K>(a, one ? d1r : d0r, one ? d1i : d0i, regmask);
         }
     }
 }
 
-/* ---- the fused pass ------------------------------------------------------------------ */
+/* ---- the fused pass ------------------------------------------------------------------
+ * Persistent CTAs: the grid is (#SMs x resident CTAs) and every CTA walks over tiles
+ * blockIdx.x, blockIdx.x + gridDim.x, ...  What depends only on the pass — the global
+ * offsets of the tile's contiguous runs and, per stage and thread, the thread's base
+ * element — is computed once per CTA into shared
+ * memory (profiles/r1b: recomputing it per stage per tile was 37% of all instructions). */
 
 template <typename real, int K, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
@@ -150,17 +186,11 @@ tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
     typedef typename Cplx<real>::type cplx;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int T = prog.T, L = prog.L;
-    cplx *tile = reinterpret_cast<cplx *>(smem_raw);
-    uint64_t *choff = reinterpret_cast<uint64_t *>(smem_raw + (sizeof(cplx) << T));
+    cplx *tile = reinterpret_cast<cplx *>(smem_raw); /* two tile buffers */
+    uint64_t *choff = reinterpret_cast<uint64_t *>(smem_raw + 2 * (sizeof(cplx) << T));
+    uint16_t *lut = reinterpret_cast<uint16_t *>(choff + (1u << (T - L)));
     const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
 
-    /* index of this CTA's tile origin: blockIdx bits deposited on the non-tile lanes */
-    uint64_t base = 0;
-    {
-        const uint64_t bid = blockIdx.x;
-        const int nrest = prog.n_lanes - T;
-        for (int i = 0; i < nrest; ++i) base |= ((bid >> i) & 1ull) << prog.rest_lane[i];
-    }
     /* global offset of each run of 2^L contiguous amplitudes of the tile */
     {
         const uint32_t nchunks = 1u << (T - L);
@@ -170,64 +200,97 @@ tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
             choff[c] = off;
         }
     }
-    __syncthreads();
-    const uint32_t lowmask = (1u << L) - 1u;
-
-    /* global -> shared, 16 bytes per thread per request, coalesced along the low lanes */
-    if (sizeof(real) == 8) {
-#pragma unroll
-        for (int i = 0; i < (1 << K); ++i) {
-            const uint32_t e = tid + i * nthr;
-            const uint64_t g = base | choff[e >> L] | (e & lowmask);
-            tile[swz<real>(e)] = __ldcs(&amp[g]);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < (1 << K) / 2; ++i) {
-            const uint32_t e = 2u * (tid + i * nthr);
-            const uint64_t g = base | choff[e >> L] | (e & lowmask);
-            const float4 v = __ldcs(reinterpret_cast<const float4 *>(&amp[g]));
-            *reinterpret_cast<float4 *>(&tile[swz<real>(e)]) = v;
-        }
-    }
-    __syncthreads();
-
+    /* per stage: this thread's base element */
     for (int s = 0; s < prog.n_stages; ++s) {
         const Stage &st = prog.stage[s];
-        if (st.op_begin == st.op_end) continue;
         uint32_t ebase = 0;
         for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
-        uint32_t rb[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) rb[j] = 1u << st.R[j];
+        lut[s * nthr + tid] = (uint16_t)ebase;
+    }
+    __syncthreads();
+    const uint32_t lowmask = (1u << L) - 1u;
+    const int nrest = prog.n_lanes - T;
+    const uint64_t n_tiles = 1ull << nrest;
 
-        cplx a[1 << K];
+    /* index of a tile's origin: tile number bits deposited on the non-tile lanes */
+    auto tile_base = [&](uint64_t t) {
+        uint64_t base = 0;
+        for (int i = 0; i < nrest; ++i) base |= ((t >> i) & 1ull) << prog.rest_lane[i];
+        return base;
+    };
+    /* global -> shared without register staging (cp.async, 16 bytes per request, coalesced
+     * along the low lanes); the copy of tile i+1 runs under the stages of tile i */
+    auto prefetch = [&](uint64_t t, cplx *dst) {
+        const uint64_t base = tile_base(t);
+        if (sizeof(real) == 8) {
 #pragma unroll
-        for (int r = 0; r < (1 << K); ++r) a[r] = tile[swz<real>(ebase | reg_offset<K>(r, rb))];
-
-        for (int o = st.op_begin; o < st.op_end; ++o) apply_op<real, K>(a, prog.op[o], base, ebase);
-
+            for (int i = 0; i < (1 << K); ++i) {
+                const uint32_t e = tid + i * nthr;
+                const uint64_t g = base | choff[e >> L] | (e & lowmask);
+                cp_async16(&dst[swz<real>(e)], &amp[g]);
+            }
+        } else {
 #pragma unroll
-        for (int r = 0; r < (1 << K); ++r) tile[swz<real>(ebase | reg_offset<K>(r, rb))] = a[r];
+            for (int i = 0; i < (1 << K) / 2; ++i) {
+                const uint32_t e = 2u * (tid + i * nthr);
+                const uint64_t g = base | choff[e >> L] | (e & lowmask);
+                cp_async16(&dst[swz<real>(e)], &amp[g]);
+            }
+        }
+    };
+
+    cplx *buf = tile;                     /* tile being worked on */
+    cplx *other = tile + (1u << T);       /* tile in flight       */
+    if (blockIdx.x < n_tiles) prefetch(blockIdx.x, buf);
+    cp_async_commit();
+
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        if (t + gridDim.x < n_tiles) prefetch(t + gridDim.x, other);
+        cp_async_commit();
+        cp_async_wait<1>(); /* everything but the newest group has landed: this tile is here */
         __syncthreads();
-    }
+        const uint64_t base = tile_base(t);
 
-    /* shared -> global */
-    if (sizeof(real) == 8) {
+        for (int s = 0; s < prog.n_stages; ++s) {
+            const Stage &st = prog.stage[s];
+            if (st.op_begin == st.op_end) continue;
+            const uint32_t ebase = lut[s * nthr + tid];
+            const uint32_t sbase = swz<real>(ebase);
+
+            cplx a[1 << K];
 #pragma unroll
-        for (int i = 0; i < (1 << K); ++i) {
-            const uint32_t e = tid + i * nthr;
-            const uint64_t g = base | choff[e >> L] | (e & lowmask);
-            __stcs(&amp[g], tile[swz<real>(e)]);
-        }
-    } else {
+            for (int r = 0; r < (1 << K); ++r) a[r] = buf[sbase ^ st.sro[r]];
+
+            for (int o = st.op_begin; o < st.op_end; ++o) apply_op<real, K>(a, prog.op[o], base, ebase);
+
 #pragma unroll
-        for (int i = 0; i < (1 << K) / 2; ++i) {
-            const uint32_t e = 2u * (tid + i * nthr);
-            const uint64_t g = base | choff[e >> L] | (e & lowmask);
-            __stcs(reinterpret_cast<float4 *>(&amp[g]), *reinterpret_cast<const float4 *>(&tile[swz<real>(e)]));
+            for (int r = 0; r < (1 << K); ++r) buf[sbase ^ st.sro[r]] = a[r];
+            __syncthreads();
         }
+
+        /* shared -> global */
+        if (sizeof(real) == 8) {
+#pragma unroll
+            for (int i = 0; i < (1 << K); ++i) {
+                const uint32_t e = tid + i * nthr;
+                const uint64_t g = base | choff[e >> L] | (e & lowmask);
+                __stcs(&amp[g], buf[swz<real>(e)]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < (1 << K) / 2; ++i) {
+                const uint32_t e = 2u * (tid + i * nthr);
+                const uint64_t g = base | choff[e >> L] | (e & lowmask);
+                __stcs(reinterpret_cast<float4 *>(&amp[g]),
+                       *reinterpret_cast<const float4 *>(&buf[swz<real>(e)]));
+            }
+        }
+        __syncthreads(); /* the prefetch after next overwrites what these stores read */
+        cplx *tmp = buf;
+        buf = other;
+        other = tmp;
     }
+    cp_async_wait<0>();
 }
 
 /* ---- one gate per launch (small state vectors) ------------------------------------------ */
@@ -261,10 +324,14 @@ simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs
     amp[i1] = o1;
 }
 
+int g_sm_count = 148;
+
 template <typename real, int K, int NT, int MINB>
 cudaError_t launch_variant(const PassProgram<real> &prog, void *amp, size_t smem, cudaStream_t stream) {
     const unsigned nthr = 1u << (prog.T - K);
-    const unsigned nblocks = 1u << (prog.n_lanes - prog.T);
+    const uint64_t n_tiles = 1ull << (prog.n_lanes - prog.T);
+    const uint64_t resident = (uint64_t)g_sm_count * MINB;
+    const unsigned nblocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
     tile_pass_kernel<real, K, NT, MINB><<<nblocks, nthr, smem, stream>>>(
         prog, reinterpret_cast<typename Cplx<real>::type *>(amp));
     return cudaGetLastError();
@@ -278,16 +345,15 @@ cudaError_t configure_variant(int max_smem_optin) {
 
 } // namespace
 
-size_t tile_pass_smem_bytes(int prec, int T, int L) {
+size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages) {
     const size_t elem = prec == 1 ? 16 : 8;
-    return (elem << T) + (sizeof(uint64_t) << (T - L));
+    const int K = prec == 1 ? QGB_K64 : QGB_K32;
+    return 2 * (elem << T) + (sizeof(uint64_t) << (T - L)) + sizeof(uint16_t) * ((size_t)n_stages << (T - K));
 }
 
-#define QGB_K64 3
-#define QGB_K32 4
-
-cudaError_t tile_pass_configure(int max_smem_optin) {
+cudaError_t tile_pass_configure(int max_smem_optin, int sm_count) {
     cudaError_t rc;
+    if (sm_count > 0) g_sm_count = sm_count;
     if ((rc = configure_variant<double, QGB_K64, 256, 3>(max_smem_optin)) != cudaSuccess) return rc;
     if ((rc = configure_variant<double, QGB_K64, 512, 2>(max_smem_optin)) != cudaSuccess) return rc;
     if ((rc = configure_variant<double, QGB_K64, 1024, 1>(max_smem_optin)) != cudaSuccess) return rc;
@@ -300,7 +366,7 @@ cudaError_t tile_pass_configure(int max_smem_optin) {
 template <>
 cudaError_t launch_tile_pass<double>(const PassProgram<double> &prog, void *amp, cudaStream_t stream) {
     if (prog.K != QGB_K64 || prog.T < prog.K || prog.T - prog.K > 10) return cudaErrorInvalidValue;
-    const size_t smem = tile_pass_smem_bytes(1, prog.T, prog.L);
+    const size_t smem = tile_pass_smem_bytes(1, prog.T, prog.L, prog.n_stages);
     const int nthr = 1 << (prog.T - prog.K);
     if (nthr <= 256) return launch_variant<double, QGB_K64, 256, 3>(prog, amp, smem, stream);
     if (nthr <= 512) return launch_variant<double, QGB_K64, 512, 2>(prog, amp, smem, stream);
@@ -311,7 +377,7 @@ template <>
 cudaError_t launch_tile_pass<float>(const PassProgram<float> &prog, void *amp, cudaStream_t stream) {
     if (prog.K != QGB_K32 || prog.T < prog.K || prog.T - prog.K > 10 || prog.L < 1)
         return cudaErrorInvalidValue;
-    const size_t smem = tile_pass_smem_bytes(2, prog.T, prog.L);
+    const size_t smem = tile_pass_smem_bytes(2, prog.T, prog.L, prog.n_stages);
     const int nthr = 1 << (prog.T - prog.K);
     if (nthr <= 256) return launch_variant<float, QGB_K32, 256, 3>(prog, amp, smem, stream);
     if (nthr <= 512) return launch_variant<float, QGB_K32, 512, 2>(prog, amp, smem, stream);

@@ -214,6 +214,12 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         for (int b = 0; b < T; ++b)
             if (used[b]) st.R[j++] = (int8_t)b;
         choose_thread_bits(st.R, K, T, cfg.fp32, st.W);
+        for (int r = 0; r < (1 << K); ++r) {
+            uint32_t roff = 0;
+            for (int jj = 0; jj < K; ++jj)
+                if (r & (1 << jj)) roff |= 1u << st.R[jj];
+            st.sro[r] = (uint16_t)tile_swizzle(roff, cfg.fp32);
+        }
         st.op_begin = st.op_end = 0;
     }
 
@@ -282,6 +288,12 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             op.bit = regbit(g.target);
             for (int e = 0; e < 8; ++e) op.m[e] = (real)g.m[e];
         }
+        if (op.kind == OP_GEN)
+            op.arm = ARM_GEN(op.bit);
+        else if (op.kind == OP_SWAP)
+            op.arm = ARM_SWAP(op.bit);
+        else
+            op.arm = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
         /* split the in-tile control predicate into its thread part and its register part */
         uint32_t rmask = 0;
         for (int j = 0; j < K; ++j) rmask |= 1u << st.R[j];

@@ -29,6 +29,12 @@ enum OpKind : int {
     OP_SWAP = 5,     /* exchange the two amplitudes of register bit `bit` (X, CX, CCX ...)    */
 };
 
+/* Op::arm bits: GEN on register bit j = 1 << j, SWAP on register bit j = 16 << j */
+#define ARM_GEN(j) (1u << (j))
+#define ARM_SWAP(j) (16u << (j))
+#define ARM_DIAG_REG 256u   /* diagonal, target on a register bit                         */
+#define ARM_DIAG_THR 512u   /* diagonal / phase, target on a thread bit or outside the tile */
+
 #define QGB_MAX_TILE_LANES 14
 #define QGB_MAX_REG_BITS 4
 #define QGB_MAX_LANES 40
@@ -46,15 +52,29 @@ struct Op {
     uint32_t cmt;         /* controls on thread bits, tile-bit coordinates                 */
     uint32_t regmask;     /* bit r set: register index r satisfies the register-bit        */
                           /* controls (GEN / SWAP: tested for the pair's low index)        */
+    uint32_t arm;         /* one-hot code path selector, see ARM_* (the kernel tests bits  */
+                          /* instead of switching on kind/bit: no jump table, the op loop  */
+                          /* stays on the uniform datapath)                                */
     uint32_t tsel;        /* OP_DIAG: tile-bit mask of the target when it is a thread bit  */
     uint32_t regsel;      /* OP_DIAG: register indices whose target bit is 1               */
     uint64_t ctrl_out;    /* controls outside the tile, state-vector index coordinates     */
 };
 
+/* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
+ * (byte address bits [6:4] ^= bits [9:7]).  Linear over GF(2), so
+ * swizzle(a | b) == swizzle(a) ^ swizzle(b) for disjoint a, b. */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t tile_swizzle(uint32_t e, bool fp32) {
+    return fp32 ? (e ^ (((e >> 4) & 7u) << 1)) : (e ^ ((e >> 3) & 7u));
+}
+
 struct Stage {
     int16_t op_begin, op_end;
     int8_t R[QGB_MAX_REG_BITS];           /* register bit j  <-> tile bit R[j], ascending   */
     int8_t W[QGB_MAX_TILE_LANES];         /* thread bit i    <-> tile bit W[i]              */
+    uint16_t sro[1 << QGB_MAX_REG_BITS];  /* swizzled tile offset of register index r       */
 };
 
 template <typename real>

@@ -62,6 +62,8 @@ def create_qubits_states_getter(dtype):
 
 
 def __getattr__(name):
+    if name == 'api':
+        return _module.api
     if name in ('initialized', 'device_ids', 'max_po2idx_per_chunk', 'memory_store_size',
                 'native_instances'):
         return getattr(_module, name)

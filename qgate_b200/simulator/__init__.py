@@ -7,7 +7,14 @@ from .simulator import Simulator
 
 
 def cuda(**prefs):
+    """One process drives one GPU.  Inside an initialised torch.distributed job (torchrun, one
+    rank per GPU) big state vectors are sharded over the ranks (qgate_b200/dist.py)."""
+    import sys
     from .. import cudaruntime
+    td = sys.modules.get('torch.distributed')
+    if td is not None and td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+        from .. import dist
+        return Simulator(dist.runtime(cudaruntime, **prefs.pop('sharding', {})), **prefs)
     return Simulator(cudaruntime, **prefs)
 
 

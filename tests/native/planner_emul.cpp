@@ -66,6 +66,12 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
             std::vector<int> seen(tile_size, 0);
             uint32_t rb[QGB_MAX_REG_BITS];
             for (int j = 0; j < K; ++j) rb[j] = 1u << st.R[j];
+            for (int r = 0; r < (1 << K); ++r) {
+                uint32_t o = 0;
+                for (int j = 0; j < K; ++j)
+                    if (r & (1 << j)) o |= rb[j];
+                CHECK(st.sro[r] == tile_swizzle(o, sizeof(real) == 4), "stage %d: bad swizzled offset of register %d", s, r);
+            }
             for (uint32_t tid = 0; tid < (1u << (T - K)); ++tid) {
                 uint32_t ebase = 0;
                 for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
@@ -86,6 +92,13 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     const Op<real> &op = p.op[o];
                     if ((base & op.ctrl_out) != op.ctrl_out) continue;
                     CHECK((op.cmt & rmask) == 0, "thread-part controls overlap the register bits");
+                    {
+                        uint32_t want = 0;
+                        if (op.kind == OP_GEN) want = ARM_GEN(op.bit);
+                        else if (op.kind == OP_SWAP) want = ARM_SWAP(op.bit);
+                        else want = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
+                        CHECK(op.arm == want, "arm selector %u of op kind %d bit %d", op.arm, op.kind, op.bit);
+                    }
                     const bool active = (ebase & op.cmt) == op.cmt;
                     const cd m0(op.m[0], op.m[1]), m1(op.m[2], op.m[3]), m2(op.m[4], op.m[5]),
                         m3(op.m[6], op.m[7]);
