@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--option', action='append', default=[], help='engine option name=value')
+    ap.add_argument('--exchange', default='auto', choices=('auto', 'p2p', 'collective'),
+                    help='lane exchange engine of the sharded runs')
     return ap.parse_args()
 
 
@@ -306,7 +308,6 @@ def main():
     gates = random_circuit_gates(n, args.depth, args.seed)
     upd = updates_of(gates, n)
 
-    stream = torch.cuda.Stream()
     clocks = ClockSampler(local_rank)
 
     def barrier():
@@ -318,13 +319,18 @@ def main():
     # -- device-timed leg: native layer, gates queued first, events around the flush ------------
     if distributed:
         from qgate_b200 import dist as qdist
-        runtime = qdist.runtime(cudaruntime)
+        runtime = qdist.runtime(cudaruntime, exchange=args.exchange)
+        runtime.ctx.bind_stream()              # NCCL work and the engine share this stream
+        runtime.ctx.timing = True
+        stream = runtime.ctx.stream
     else:
         runtime = cudaruntime
+        stream = torch.cuda.Stream()
     qstates = runtime.create_qubit_states(dtype)
     proc = qstates.processor
     proc.initialize_qubit_states(qstates, n)
-    api.set_stream(stream.cuda_stream)
+    if not distributed:
+        api.set_stream(stream.cuda_stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def device_step():
@@ -339,6 +345,10 @@ def main():
         proc.flush(qstates)
     barrier()
     api.stats_reset()
+    if distributed:
+        runtime.ctx.exchange_ms()
+        for key in runtime.ctx.stats:
+            runtime.ctx.stats[key] = 0
     clocks.start()
     device_ms = 0.
     for _ in range(args.steps):
@@ -361,7 +371,7 @@ def main():
     tile_passes = stats['tile_passes']
     launches = stats['kernel_launches']
     pass_bytes = 2 * (elem << args.qubits)
-    exch_ms = stats.get('exchange_ms', 0.) if isinstance(stats, dict) else 0.
+    exch_ms = runtime.ctx.exchange_ms() if distributed else 0.
     avg_pass_ms = (device_ms - exch_ms) / max(1, tile_passes)
     peak, peak_src = measured_peak()
     achieved = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
@@ -370,7 +380,21 @@ def main():
                 'peak_source': peak_src, 'bytes_per_launch': pass_bytes,
                 'avg_launch_ms': avg_pass_ms, 'launches_per_step': tile_passes / args.steps,
                 'gates_per_launch': len(gates) * args.steps / max(1, tile_passes)}
-    api.set_stream(0)
+    nvlink = None
+    if distributed:
+        dstats = runtime.ctx.stats
+        if dstats['exchanges']:
+            # bytes each GPU sends (= receives) per exchange over its NVLink ports
+            gbs = dstats['exchange_bytes'] / (exch_ms * 1e-3) / 1e9
+            nvlink = {'exchange': runtime.ctx.exchange, 'exchanges_per_step': dstats['exchanges'] / args.steps,
+                      'lanes_per_exchange': dstats['exchange_lanes'] / dstats['exchanges'],
+                      'local_swaps_per_step': dstats['local_swaps'] / args.steps,
+                      'bytes_per_gpu_per_direction_per_step': dstats['exchange_bytes'] // args.steps,
+                      'ms_per_step': exch_ms / args.steps, 'achieved': gbs, 'unit': 'GB/s',
+                      'peak': 770., 'frac': gbs / 770.,
+                      'peak_source': 'measured peer copy per direction (B200_PROFILING.md)'}
+    else:
+        api.set_stream(0)
     qstates.delete()
     del qstates, proc
 
@@ -433,7 +457,7 @@ def main():
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
                 'config': config, 'clocks': clock_info, 'e2e': e2e,
                 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
-                'hbm_gbs_per_gpu': achieved,
+                'hbm_gbs_per_gpu': achieved, 'nvlink': nvlink,
                 'gates': len(gates), 'p0_check': p0}
         print(json.dumps(line))
     if distributed:

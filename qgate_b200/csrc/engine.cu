@@ -201,6 +201,8 @@ struct Options {
     int64_t max_cost = 1 << 30;
     int64_t lookahead = 4096;
     int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
+    int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
+    int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
 };
 
 struct Engine {
@@ -277,7 +279,8 @@ void flush_tiled(QStates *qs) {
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
-    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
+    const int n_buf = g.opt.tile_buffers == 2 ? 2 : 1;
+    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1, 8, n_buf) > (size_t)g.max_smem_optin) --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
     if (cfg.T >= qs->n_lanes) cfg.L = std::min((int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64), cfg.T);
@@ -286,10 +289,11 @@ void flush_tiled(QStates *qs) {
         /* stages: each costs a per-thread table entry in shared memory; keep the CTA small enough
          * for the occupancy its launch bounds ask for (3 / 2 / 1 CTAs per SM) */
         const int nthr = 1 << (cfg.T - cfg.K);
-        const int want_ctas = nthr <= 256 ? 3 : (nthr <= 512 ? 2 : 1);
-        const size_t budget = (size_t)g.max_smem_optin / want_ctas - 1024;
+        int want_ctas = nthr <= 256 ? (n_buf == 2 ? 3 : 4) : (nthr <= 512 ? 2 : 1);
+        if (g.opt.ctas_per_sm > 0) want_ctas = (int)g.opt.ctas_per_sm;
+        const size_t budget = (size_t)(g.max_smem_optin + 1024) / want_ctas - 1024;
         int ms = QGB_MAX_STAGES;
-        while (ms > 2 && tile_pass_smem_bytes(qs->prec, cfg.T, cfg.L, ms) > budget) --ms;
+        while (ms > 2 && tile_pass_smem_bytes(qs->prec, cfg.T, cfg.L, ms, n_buf) > budget) --ms;
         cfg.max_stages = ms;
     }
     cfg.max_cost = (int)g.opt.max_cost;
@@ -299,7 +303,7 @@ void flush_tiled(QStates *qs) {
     while (!qs->queue.empty()) {
         plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
         if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
-        CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, g.stream));
+        CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, n_buf, g.stream));
         g.stats.kernel_launches += 1;
         g.stats.tile_passes += 1;
         g.stats.gates_executed += st.gates_in_pass;
@@ -1186,6 +1190,8 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "max_cost") g.opt.max_cost = value;
     else if (k == "lookahead") g.opt.lookahead = value;
     else if (k == "queue_limit") g.opt.queue_limit = value;
+    else if (k == "tile_buffers") g.opt.tile_buffers = value;
+    else if (k == "ctas_per_sm") g.opt.ctas_per_sm = value;
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH
 }

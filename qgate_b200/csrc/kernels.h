@@ -33,10 +33,12 @@ struct GatherParams {
 };
 
 /* ---- gates ----------------------------------------------------------------------- */
+/* n_buf: 1 = one tile buffer per CTA (more resident CTAs), 2 = the next tile is prefetched
+ * while the current one is worked on */
 template <typename real>
-cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, cudaStream_t stream);
-/* smem bytes the tile kernel needs for (T, L) and n_stages stages */
-size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages);
+cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, int n_buf, cudaStream_t stream);
+/* smem bytes the tile kernel needs for (T, L), n_stages stages and n_buf tile buffers */
+size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages, int n_buf);
 cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,

@@ -91,6 +91,23 @@ __device__ __forceinline__ void apply_gen(typename Cplx<real>::type (&a)[1 << K]
         apply_gen_pairs<real, K, J, false>(a, m, regmask);
 }
 
+/* multiplexed by a register bit: the pairs of `regsel` take m1, the others m (uniform choice) */
+template <typename real, int K, int J>
+__device__ __forceinline__ void apply_gen_mux_reg(typename Cplx<real>::type (&a)[1 << K], const real *m,
+                                                  const real *m1, uint32_t regsel) {
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        const int r1 = r0 | (1 << J);
+        const real *mm = (regsel & (1u << r0)) ? m1 : m;
+        const real q0r = a[r0].x, q0i = a[r0].y, q1r = a[r1].x, q1i = a[r1].y;
+        a[r0].x = mm[0] * q0r - mm[1] * q0i + mm[2] * q1r - mm[3] * q1i;
+        a[r0].y = mm[0] * q0i + mm[1] * q0r + mm[2] * q1i + mm[3] * q1r;
+        a[r1].x = mm[4] * q0r - mm[5] * q0i + mm[6] * q1r - mm[7] * q1i;
+        a[r1].y = mm[4] * q0i + mm[5] * q0r + mm[6] * q1i + mm[7] * q1r;
+    }
+}
+
 template <typename real, int K, int J>
 __device__ __forceinline__ void apply_swap(typename Cplx<real>::type (&a)[1 << K], uint32_t regmask,
                                            bool active) {
@@ -135,16 +152,33 @@ __device__ __forceinline__ void apply_op(typename Cplx<real>::type (&a)[1 << K],
     const uint32_t regmask = op.regmask;
     const uint32_t arm = op.arm;
     if (arm & (ARM_GEN(0) | ARM_GEN(1) | ARM_GEN(2) | ARM_GEN(3))) {
-        if (op.cmt == 0) {
-            /* no thread-bit controls (the usual case): the matrix stays in uniform registers */
-            if (arm & ARM_GEN(0)) apply_gen<real, K, 0>(a, op.m, regmask);
-            if (K > 1 && (arm & ARM_GEN(1))) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, op.m, regmask);
-            if (K > 2 && (arm & ARM_GEN(2))) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, op.m, regmask);
-            if (K > 3 && (arm & ARM_GEN(3))) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, op.m, regmask);
+        if (arm & ARM_MUX_REG) {
+            const uint32_t regsel = op.regsel;
+            if (arm & ARM_GEN(0)) apply_gen_mux_reg<real, K, 0>(a, op.m, op.m1, regsel);
+            if (K > 1 && (arm & ARM_GEN(1))) apply_gen_mux_reg<real, K, (K > 1 ? 1 : 0)>(a, op.m, op.m1, regsel);
+            if (K > 2 && (arm & ARM_GEN(2))) apply_gen_mux_reg<real, K, (K > 2 ? 2 : 0)>(a, op.m, op.m1, regsel);
+            if (K > 3 && (arm & ARM_GEN(3))) apply_gen_mux_reg<real, K, (K > 3 ? 3 : 0)>(a, op.m, op.m1, regsel);
+        } else if (op.cmt == 0 && !(arm & ARM_MUX_THR)) {
+            /* no thread-bit controls (the usual case): the matrix stays in uniform registers;
+             * a multiplexer outside the tile picks the matrix once per CTA */
+            const real *mm = op.m;
+            if ((arm & ARM_MUX_OUT) && ((base >> op.mux_out) & 1ull)) mm = op.m1;
+            if (arm & ARM_GEN(0)) apply_gen<real, K, 0>(a, mm, regmask);
+            if (K > 1 && (arm & ARM_GEN(1))) apply_gen<real, K, (K > 1 ? 1 : 0)>(a, mm, regmask);
+            if (K > 2 && (arm & ARM_GEN(2))) apply_gen<real, K, (K > 2 ? 2 : 0)>(a, mm, regmask);
+            if (K > 3 && (arm & ARM_GEN(3))) apply_gen<real, K, (K > 3 ? 3 : 0)>(a, mm, regmask);
         } else {
+            /* per-thread matrix: multiplexed by a thread bit, or the identity for the threads whose
+             * thread-bit controls are not satisfied */
             real m[8];
+            if (arm & ARM_MUX_THR) {
+                const bool one = (ebase & op.tsel) != 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) m[i] = active ? op.m[i] : ((i == 0 || i == 6) ? (real)1 : (real)0);
+                for (int i = 0; i < 8; ++i) m[i] = one ? op.m1[i] : op.m[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) m[i] = active ? op.m[i] : ((i == 0 || i == 6) ? (real)1 : (real)0);
+            }
             if (arm & ARM_GEN(0)) apply_gen_pairs<real, K, 0, false>(a, m, regmask);
             if (K > 1 && (arm & ARM_GEN(1))) apply_gen_pairs<real, K, (K > 1 ? 1 : 0), false>(a, m, regmask);
             if (K > 2 && (arm & ARM_GEN(2))) apply_gen_pairs<real, K, (K > 2 ? 2 : 0), false>(a, m, regmask);
@@ -179,15 +213,15 @@ __device__ __forceinline__ void apply_op(typename Cplx<real>::type (&a)[1 << K],
  * element — is computed once per CTA into shared
  * memory (profiles/r1b: recomputing it per stage per tile was 37% of all instructions). */
 
-template <typename real, int K, int NT, int MINB>
+template <typename real, int K, int NT, int MINB, int NBUF>
 __global__ void __launch_bounds__(NT, MINB)
 tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
                  typename Cplx<real>::type *__restrict__ amp) {
     typedef typename Cplx<real>::type cplx;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int T = prog.T, L = prog.L;
-    cplx *tile = reinterpret_cast<cplx *>(smem_raw); /* two tile buffers */
-    uint64_t *choff = reinterpret_cast<uint64_t *>(smem_raw + 2 * (sizeof(cplx) << T));
+    cplx *tile = reinterpret_cast<cplx *>(smem_raw); /* NBUF tile buffers */
+    uint64_t *choff = reinterpret_cast<uint64_t *>(smem_raw + NBUF * (sizeof(cplx) << T));
     uint16_t *lut = reinterpret_cast<uint16_t *>(choff + (1u << (T - L)));
     const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
 
@@ -240,14 +274,22 @@ tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
     };
 
     cplx *buf = tile;                     /* tile being worked on */
-    cplx *other = tile + (1u << T);       /* tile in flight       */
-    if (blockIdx.x < n_tiles) prefetch(blockIdx.x, buf);
-    cp_async_commit();
+    cplx *other = tile + (NBUF == 2 ? (1u << T) : 0u); /* tile in flight (NBUF == 2) */
+    if (NBUF == 2) {
+        if (blockIdx.x < n_tiles) prefetch(blockIdx.x, buf);
+        cp_async_commit();
+    }
 
     for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        if (t + gridDim.x < n_tiles) prefetch(t + gridDim.x, other);
-        cp_async_commit();
-        cp_async_wait<1>(); /* everything but the newest group has landed: this tile is here */
+        if (NBUF == 2) {
+            if (t + gridDim.x < n_tiles) prefetch(t + gridDim.x, other);
+            cp_async_commit();
+            cp_async_wait<1>(); /* everything but the newest group has landed: this tile is here */
+        } else {
+            prefetch(t, buf);   /* one buffer: the other resident CTAs cover the latency */
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         __syncthreads();
         const uint64_t base = tile_base(t);
 
@@ -285,10 +327,12 @@ tile_pass_kernel(const __grid_constant__ PassProgram<real> prog,
                        *reinterpret_cast<const float4 *>(&buf[swz<real>(e)]));
             }
         }
-        __syncthreads(); /* the prefetch after next overwrites what these stores read */
-        cplx *tmp = buf;
-        buf = other;
-        other = tmp;
+        __syncthreads(); /* the next prefetch into this buffer overwrites what these stores read */
+        if (NBUF == 2) {
+            cplx *tmp = buf;
+            buf = other;
+            other = tmp;
+        }
     }
     cp_async_wait<0>();
 }
@@ -325,63 +369,72 @@ simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs
 }
 
 int g_sm_count = 148;
+int g_max_smem = 48 * 1024;
 
-template <typename real, int K, int NT, int MINB>
+/* Launch bounds: every variant is capped at 64 registers per thread (NT x MINB = 1024 threads per
+ * SM).  With more registers available ptxas preloads the 2x2 matrices into vector registers
+ * (LDC + moves) instead of reading them from uniform registers (profiles/r1d). */
+template <typename real, int K, int NT, int MINB, int NBUF>
 cudaError_t launch_variant(const PassProgram<real> &prog, void *amp, size_t smem, cudaStream_t stream) {
+    static int configured = 0;
+    auto kernel = tile_pass_kernel<real, K, NT, MINB, NBUF>;
+    if (!configured) {
+        cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem);
+        if (rc != cudaSuccess) return rc;
+        configured = 1;
+    }
     const unsigned nthr = 1u << (prog.T - K);
+    int per_sm = 0;
+    cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)nthr, smem);
+    if (rc != cudaSuccess) return rc;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     const uint64_t n_tiles = 1ull << (prog.n_lanes - prog.T);
-    const uint64_t resident = (uint64_t)g_sm_count * MINB;
+    const uint64_t resident = (uint64_t)g_sm_count * per_sm; /* persistent: one wave */
     const unsigned nblocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
-    tile_pass_kernel<real, K, NT, MINB><<<nblocks, nthr, smem, stream>>>(
-        prog, reinterpret_cast<typename Cplx<real>::type *>(amp));
+    kernel<<<nblocks, nthr, smem, stream>>>(prog, reinterpret_cast<typename Cplx<real>::type *>(amp));
     return cudaGetLastError();
 }
 
-template <typename real, int K, int NT, int MINB>
-cudaError_t configure_variant(int max_smem_optin) {
-    return cudaFuncSetAttribute(tile_pass_kernel<real, K, NT, MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin);
+template <typename real, int K>
+cudaError_t launch_by_shape(const PassProgram<real> &prog, void *amp, int prec, int n_buf, cudaStream_t stream) {
+    const size_t smem = tile_pass_smem_bytes(prec, prog.T, prog.L, prog.n_stages, n_buf);
+    const int nthr = 1 << (prog.T - prog.K);
+    if (n_buf == 2) {
+        if (nthr <= 256) return launch_variant<real, K, 256, 4, 2>(prog, amp, smem, stream);
+        if (nthr <= 512) return launch_variant<real, K, 512, 2, 2>(prog, amp, smem, stream);
+        return launch_variant<real, K, 1024, 1, 2>(prog, amp, smem, stream);
+    }
+    if (nthr <= 256) return launch_variant<real, K, 256, 4, 1>(prog, amp, smem, stream);
+    if (nthr <= 512) return launch_variant<real, K, 512, 2, 1>(prog, amp, smem, stream);
+    return launch_variant<real, K, 1024, 1, 1>(prog, amp, smem, stream);
 }
 
 } // namespace
 
-size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages) {
+size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages, int n_buf) {
     const size_t elem = prec == 1 ? 16 : 8;
     const int K = prec == 1 ? QGB_K64 : QGB_K32;
-    return 2 * (elem << T) + (sizeof(uint64_t) << (T - L)) + sizeof(uint16_t) * ((size_t)n_stages << (T - K));
+    return n_buf * (elem << T) + (sizeof(uint64_t) << (T - L)) +
+           sizeof(uint16_t) * ((size_t)n_stages << (T - K));
 }
 
 cudaError_t tile_pass_configure(int max_smem_optin, int sm_count) {
-    cudaError_t rc;
     if (sm_count > 0) g_sm_count = sm_count;
-    if ((rc = configure_variant<double, QGB_K64, 256, 3>(max_smem_optin)) != cudaSuccess) return rc;
-    if ((rc = configure_variant<double, QGB_K64, 512, 2>(max_smem_optin)) != cudaSuccess) return rc;
-    if ((rc = configure_variant<double, QGB_K64, 1024, 1>(max_smem_optin)) != cudaSuccess) return rc;
-    if ((rc = configure_variant<float, QGB_K32, 256, 3>(max_smem_optin)) != cudaSuccess) return rc;
-    if ((rc = configure_variant<float, QGB_K32, 512, 2>(max_smem_optin)) != cudaSuccess) return rc;
-    if ((rc = configure_variant<float, QGB_K32, 1024, 1>(max_smem_optin)) != cudaSuccess) return rc;
+    g_max_smem = max_smem_optin;
     return cudaSuccess;
 }
 
 template <>
-cudaError_t launch_tile_pass<double>(const PassProgram<double> &prog, void *amp, cudaStream_t stream) {
+cudaError_t launch_tile_pass<double>(const PassProgram<double> &prog, void *amp, int n_buf, cudaStream_t stream) {
     if (prog.K != QGB_K64 || prog.T < prog.K || prog.T - prog.K > 10) return cudaErrorInvalidValue;
-    const size_t smem = tile_pass_smem_bytes(1, prog.T, prog.L, prog.n_stages);
-    const int nthr = 1 << (prog.T - prog.K);
-    if (nthr <= 256) return launch_variant<double, QGB_K64, 256, 3>(prog, amp, smem, stream);
-    if (nthr <= 512) return launch_variant<double, QGB_K64, 512, 2>(prog, amp, smem, stream);
-    return launch_variant<double, QGB_K64, 1024, 1>(prog, amp, smem, stream);
+    return launch_by_shape<double, QGB_K64>(prog, amp, 1, n_buf == 2 ? 2 : 1, stream);
 }
 
 template <>
-cudaError_t launch_tile_pass<float>(const PassProgram<float> &prog, void *amp, cudaStream_t stream) {
+cudaError_t launch_tile_pass<float>(const PassProgram<float> &prog, void *amp, int n_buf, cudaStream_t stream) {
     if (prog.K != QGB_K32 || prog.T < prog.K || prog.T - prog.K > 10 || prog.L < 1)
         return cudaErrorInvalidValue;
-    const size_t smem = tile_pass_smem_bytes(2, prog.T, prog.L, prog.n_stages);
-    const int nthr = 1 << (prog.T - prog.K);
-    if (nthr <= 256) return launch_variant<float, QGB_K32, 256, 3>(prog, amp, smem, stream);
-    if (nthr <= 512) return launch_variant<float, QGB_K32, 512, 2>(prog, amp, smem, stream);
-    return launch_variant<float, QGB_K32, 1024, 1>(prog, amp, smem, stream);
+    return launch_by_shape<float, QGB_K32>(prog, amp, 2, n_buf == 2 ? 2 : 1, stream);
 }
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,

@@ -77,24 +77,68 @@ struct Picked {
 
 } // namespace
 
+namespace {
+
+inline bool mat_is_diag(const double *m) { return m[2] == 0. && m[3] == 0. && m[4] == 0. && m[5] == 0.; }
+
+inline uint64_t touched_lanes(const Gate &p) {
+    return p.ctrl_mask | (1ull << p.target) | (p.mux >= 0 ? (1ull << p.mux) : 0ull);
+}
+
+/* does p act non-diagonally on `lane`?  (a control / multiplexer lane is acted on diagonally) */
+inline bool acts_nondiag_on(const Gate &p, int lane) { return p.target == lane && !gate_is_diag(p); }
+
+const double kIdentity[8] = {1., 0., 0., 0., 0., 0., 1., 0.};
+
+} // namespace
+
+/* Host-side merging (matrices composed in double).  The new gate g is moved BACKWARDS over the
+ * queued gates it commutes with until it meets a gate p on the same target it can fold into:
+ *   plain g (no control):      commutes with everything that does not touch its target;
+ *                              folds into a plain or multiplexed p (both branches get g.m on top);
+ *   g with one control c:      commutes with everything that neither touches its target nor acts
+ *                              non-diagonally on c; folds into a plain p (which becomes multiplexed
+ *                              by c: m1 = g.m p.m) or into a p already multiplexed by c, provided
+ *                              the result is dense (diagonal controlled gates stay cheap phases);
+ *   anything else:             folds only into an identical-signature gate directly before it. */
 bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
-    if (merge && !queue.empty()) {
-        if (g.ctrl_mask == 0) {
-            uint64_t tm = 1ull << g.target;
-            int lo = std::max(0, (int)queue.size() - 256);
+    if (merge && !queue.empty() && g.mux < 0) {
+        const int n_ctrl = popcount64(g.ctrl_mask);
+        if (n_ctrl <= 1) {
+            const uint64_t tm = 1ull << g.target;
+            const int c = n_ctrl ? __builtin_ctzll(g.ctrl_mask) : -1;
+            const int lo = std::max(0, (int)queue.size() - 256);
             for (int i = (int)queue.size() - 1; i >= lo; --i) {
                 Gate &p = queue[i];
-                uint64_t touched = p.ctrl_mask | (1ull << p.target);
-                if (!(touched & tm)) continue;
-                if (p.ctrl_mask == 0 && p.target == g.target) {
-                    matmul2(g.m, p.m, p.m);
+                if (!(touched_lanes(p) & tm)) {
+                    if (c >= 0 && acts_nondiag_on(p, c)) break; /* g does not commute with p */
+                    continue;
+                }
+                if (p.target != g.target) break;
+                if (c < 0) {
+                    if (p.ctrl_mask == 0) { /* plain or multiplexed p */
+                        matmul2(g.m, p.m, p.m);
+                        if (p.mux >= 0) matmul2(g.m, p.m1, p.m1);
+                        return true;
+                    }
+                } else if (p.ctrl_mask == g.ctrl_mask && p.mux < 0 && i == (int)queue.size() - 1) {
+                    matmul2(g.m, p.m, p.m); /* same control, same target, adjacent */
                     return true;
+                } else if (p.ctrl_mask == 0 && (p.mux < 0 || p.mux == c)) {
+                    const double *low = p.m, *high = p.mux < 0 ? p.m : p.m1;
+                    double m1[8];
+                    matmul2(g.m, high, m1);
+                    if (!(mat_is_diag(low) && mat_is_diag(m1))) {
+                        std::memcpy(p.m1, m1, sizeof(m1));
+                        p.mux = c;
+                        return true;
+                    }
                 }
                 break;
             }
         } else {
             Gate &p = queue.back();
-            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask) {
+            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask && p.mux < 0) {
                 matmul2(g.m, p.m, p.m);
                 return true;
             }
@@ -121,6 +165,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
     uint64_t blockedX = 0, blockedZ = 0;
     std::vector<Picked> picked;
     std::vector<uint64_t> stageR; /* lane masks of the register bits of each stage */
+    std::vector<uint64_t> stageMux; /* multiplexer lanes of the gates of each stage */
     int first_block = -1;
     int cost = 0;
 
@@ -130,7 +175,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         const bool diag = gate_is_diag(g);
         const uint64_t tm = 1ull << g.target;
         const uint64_t xq = diag ? 0 : tm;
-        const uint64_t zq = g.ctrl_mask | (diag ? tm : 0);
+        const uint64_t zq = g.ctrl_mask | (diag ? tm : 0) | (g.mux >= 0 ? (1ull << g.mux) : 0ull);
         bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
         const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : 4);
         if (!blocked && ((int)picked.size() >= max_ops || (cost + gcost > cfg.max_cost && !picked.empty())))
@@ -163,10 +208,13 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             S |= xq;
             ++count;
         }
-        if (action == 1)
+        if (action == 1) {
             stageR.push_back(xq);
-        else if (action == 2)
+            stageMux.push_back(0);
+        } else if (action == 2) {
             stageR.back() |= xq;
+        }
+        if (g.mux >= 0) stageMux.back() |= 1ull << g.mux;
         picked.push_back({i, (int)stageR.size() - 1});
         cost += gcost;
     }
@@ -207,7 +255,12 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         int k = 0;
         for (int lane = 0; lane < n; ++lane)
             if (Rl & (1ull << lane)) used[lane_to_tile[lane]] = true, ++k;
-        /* pad with the highest free tile bits: keeps the low (bank-selecting) bits for threads */
+        /* pad first with multiplexer lanes of this stage's gates (the matrix choice is then uniform
+         * per register pair instead of a per-thread select), then with the highest free tile
+         * bits: keeps the low (bank-selecting) bits for threads */
+        const uint64_t Ml = s < (int)stageMux.size() ? (stageMux[s] & S & ~Rl) : 0;
+        for (int lane = n - 1; lane >= 0 && k < K; --lane)
+            if ((Ml & (1ull << lane)) && !used[lane_to_tile[lane]]) used[lane_to_tile[lane]] = true, ++k;
         for (int b = T - 1; b >= 0 && k < K; --b)
             if (!used[b]) used[b] = true, ++k;
         int j = 0;
@@ -250,6 +303,8 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         op.tsel = 0;
         op.regsel = 0;
         op.bit = 0;
+        op.mux_out = 0;
+        op.pad_ = 0;
         if (gate_is_diag(g)) {
             const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
@@ -279,7 +334,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                     op.bit = g.target;
                 }
             }
-        } else if (g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
+        } else if (g.mux < 0 && g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
                    g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.) {
             op.kind = OP_SWAP;
             op.bit = regbit(g.target);
@@ -288,8 +343,27 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             op.bit = regbit(g.target);
             for (int e = 0; e < 8; ++e) op.m[e] = (real)g.m[e];
         }
+        uint32_t mux_arm = 0;
+        if (g.mux >= 0) {
+            /* multiplexed 2x2: which matrix a pair gets depends on one more lane */
+            for (int e = 0; e < 8; ++e) op.m1[e] = (real)g.m1[e];
+            if ((S >> g.mux) & 1ull) {
+                const int j = regbit(g.mux);
+                if (j >= 0) {
+                    mux_arm = ARM_MUX_REG;
+                    for (int r = 0; r < (1 << K); ++r)
+                        if (r & (1 << j)) op.regsel |= 1u << r;
+                } else {
+                    mux_arm = ARM_MUX_THR;
+                    op.tsel = 1u << lane_to_tile[g.mux];
+                }
+            } else {
+                mux_arm = ARM_MUX_OUT;
+                op.mux_out = g.mux;
+            }
+        }
         if (op.kind == OP_GEN)
-            op.arm = ARM_GEN(op.bit);
+            op.arm = ARM_GEN(op.bit) | mux_arm;
         else if (op.kind == OP_SWAP)
             op.arm = ARM_SWAP(op.bit);
         else

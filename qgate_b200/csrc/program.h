@@ -34,6 +34,9 @@ enum OpKind : int {
 #define ARM_SWAP(j) (16u << (j))
 #define ARM_DIAG_REG 256u   /* diagonal, target on a register bit                         */
 #define ARM_DIAG_THR 512u   /* diagonal / phase, target on a thread bit or outside the tile */
+#define ARM_MUX_THR 1024u   /* OP_GEN multiplexed by a thread bit (matrix chosen per thread)  */
+#define ARM_MUX_REG 2048u   /* OP_GEN multiplexed by a register bit (matrix chosen per pair)  */
+#define ARM_MUX_OUT 4096u   /* OP_GEN multiplexed by a lane outside the tile (per CTA)        */
 
 #define QGB_MAX_TILE_LANES 14
 #define QGB_MAX_REG_BITS 4
@@ -56,8 +59,14 @@ struct Op {
                           /* instead of switching on kind/bit: no jump table, the op loop  */
                           /* stays on the uniform datapath)                                */
     uint32_t tsel;        /* OP_DIAG: tile-bit mask of the target when it is a thread bit  */
+                          /* OP_GEN + ARM_MUX_THR: tile-bit mask of the multiplexer lane   */
     uint32_t regsel;      /* OP_DIAG: register indices whose target bit is 1               */
+                          /* OP_GEN + ARM_MUX_REG: pairs (low index) whose mux bit is 1    */
     uint64_t ctrl_out;    /* controls outside the tile, state-vector index coordinates     */
+    real m1[8];           /* multiplexed OP_GEN: the matrix where the multiplexer bit is 1 */
+                          /* (ARM_MUX_OUT: `mux_out` = the state-vector lane, outside tile) */
+    int32_t mux_out;
+    int32_t pad_;
 };
 
 /* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
@@ -97,9 +106,15 @@ struct Gate {
     double m[8];
     int32_t target;
     uint64_t ctrl_mask;
+    /* multiplexed form, made by the host-side merging only (planner.cpp enqueue_gate): with
+     * mux >= 0 the gate applies m where lane `mux` is 0 and m1 where it is 1 (ctrl_mask == 0).
+     * U(t) . CX(c->t) . V(t) collapses into ONE such gate: m = U V, m1 = U X V. */
+    int32_t mux = -1;
+    double m1[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
 };
 
 inline bool gate_is_diag(const Gate &g) {
+    if (g.mux >= 0) return false; /* multiplexed gates are only formed when the result is dense */
     return g.m[2] == 0. && g.m[3] == 0. && g.m[4] == 0. && g.m[5] == 0.;
 }
 inline bool gate_is_antidiag(const Gate &g) {

