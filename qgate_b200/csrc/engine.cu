@@ -321,8 +321,17 @@ void flush(QStates *qs) {
             flush_tiled<float>(qs);
     } else {
         for (const Gate &gt : qs->queue) {
-            CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, gt.ctrl_mask,
-                                          g.stream));
+            if (gt.mux >= 0) {
+                /* multiplexed gate (host-side merging): m where lane mux is 0, m1 where it is 1 */
+                CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, 0,
+                                              1ull << gt.mux, g.stream));
+                CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m1, gt.target,
+                                              1ull << gt.mux, 0, g.stream));
+                g.stats.kernel_launches += 1;
+            } else {
+                CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, gt.ctrl_mask,
+                                              0, g.stream));
+            }
             g.stats.kernel_launches += 1;
             g.stats.gates_executed += 1;
         }
@@ -342,7 +351,9 @@ void submit_gate(QStates *qs, const double *mat8, const int *ctrl, int n_ctrl, i
         if (ctrl[i] == target) fail(QGB_ERR_INVALID, "control lane equals target lane.");
         gt.ctrl_mask |= 1ull << ctrl[i];
     }
-    enqueue_gate(qs->queue, gt, g.opt.merge != 0);
+    /* merging pays on the tiled path only; the one-kernel-per-gate path keeps the submitted gates */
+    const bool tiled = g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec);
+    enqueue_gate(qs->queue, gt, g.opt.merge != 0 && tiled);
     g.stats.gates_submitted += 1;
     g.stats.gate_amp_updates += (int64_t)1 << (qs->n_lanes - n_ctrl);
     if ((int64_t)qs->queue.size() >= g.opt.queue_limit) flush(qs);

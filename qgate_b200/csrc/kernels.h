@@ -42,7 +42,7 @@ size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages, int n_buf);
 cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
-                               uint64_t ctrl_mask, cudaStream_t stream);
+                               uint64_t ctrl_mask, uint64_t zero_mask, cudaStream_t stream);
 
 /* ---- state-vector maintenance ------------------------------------------------------ */
 cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,

@@ -348,6 +348,8 @@ template <typename real>
 __global__ void __launch_bounds__(256)
 simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs, SortedBits skip,
                    uint64_t target_bit, uint64_t ctrl_mask, Mat2<real> mat) {
+    /* `skip` lists the target, the controls (deposited as 1 through ctrl_mask) and the lanes
+     * that must be 0 (a multiplexed gate's low branch): those stay 0 after the insertion */
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= n_pairs) return;
     /* insert a 0 at every skipped position (target and controls), ascending */
@@ -438,10 +440,10 @@ cudaError_t launch_tile_pass<float>(const PassProgram<float> &prog, void *amp, i
 }
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
-                               uint64_t ctrl_mask, cudaStream_t stream) {
+                               uint64_t ctrl_mask, uint64_t zero_mask, cudaStream_t stream) {
     SortedBits skip;
     skip.n = 0;
-    const uint64_t touched = ctrl_mask | (1ull << target);
+    const uint64_t touched = ctrl_mask | zero_mask | (1ull << target);
     for (int lane = 0; lane < n_lanes; ++lane)
         if (touched & (1ull << lane)) skip.pos[skip.n++] = (int8_t)lane;
     const uint64_t n_pairs = 1ull << (n_lanes - skip.n);

@@ -272,7 +272,21 @@ def test_against_reference_cpu_runtime_16_to_20_qubits(cuda_runtime, ref_runtime
         sim.terminate()
     (a, bits_a, p0_a, s_a, prob_a), (b, bits_b, p0_b, s_b, prob_b) = outs
     assert bits_a == bits_b
-    assert cases.rel_err(a, b) < cases.TOL[dtype]
+    if dtype is np.float64:
+        assert cases.rel_err(a, b) < cases.TOL[dtype]
+    else:
+        # the complex64 reference carries its own rounding error (one rounding per gate; the
+        # engine composes merged gates in double first): both are held to 1e-5 of the complex128
+        # reference, and to each other within the sum of the two errors
+        sim = cases.make_sim(ref_runtime.module, np.float64, 'one_static')
+        np.random.seed(123)
+        sim.run(ops + tail)
+        sim.qubits.set_ordering(q)
+        exact = sim.qubits.states[:]
+        sim.terminate()
+        err_ref = cases.rel_err(b, exact)
+        assert cases.rel_err(a, exact) < cases.TOL[dtype]
+        assert cases.rel_err(a, b) < cases.TOL[dtype] + err_ref
     assert np.abs(p0_a - p0_b).max() < (1e-12 if dtype is np.float64 else 1e-5)
     if dtype is np.float64:
         assert np.array_equal(s_a, s_b)
