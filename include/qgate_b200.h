@@ -242,6 +242,7 @@ typedef struct qgb_stats {
     int64_t pass_bytes;           /* algorithmic bytes of all tile passes (2*2^n*B)   */
     int64_t h2d_bytes;            /* host->device bytes moved by this library         */
     int64_t d2h_bytes;            /* device->host bytes moved by this library         */
+    int64_t tma_passes;           /* tile passes staged by TMA tensor-map copies      */
 } qgb_stats;
 int qgb_stats_get(qgb_stats *out);
 int qgb_stats_reset(void);

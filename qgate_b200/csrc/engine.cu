@@ -203,6 +203,8 @@ struct Options {
     int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
     int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
     int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
+    int64_t tma = 1;               /* 1: TMA tensor-map staging (kernels_tma.cu), 0: cp.async */
+    int64_t tma_buffers = 2;       /* tile buffers per CTA of the TMA kernel (2 or 3)         */
 };
 
 struct Engine {
@@ -279,21 +281,41 @@ void flush_tiled(QStates *qs) {
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
-    const int n_buf = g.opt.tile_buffers == 2 ? 2 : 1;
-    while (cfg.T > cfg.K + 5 && tile_pass_smem_bytes(qs->prec, cfg.T, 1, 8, n_buf) > (size_t)g.max_smem_optin) --cfg.T;
+    const bool tma = g.opt.tma != 0;
+    const int n_buf = tma ? (g.opt.tma_buffers >= 3 ? 3 : 2) : (g.opt.tile_buffers == 2 ? 2 : 1);
+    /* ops per TMA pass: their matrices are staged in shared memory (8 complex per op) */
+    const int tma_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
+    auto smem_bytes = [&](int T, int L, int stages) {
+        return tma ? tma_pass_smem_bytes(qs->prec, T, stages, n_buf, tma_ops)
+                   : tile_pass_smem_bytes(qs->prec, T, L, stages, n_buf);
+    };
+    while (cfg.T > cfg.K + 5 && smem_bytes(cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
     if (cfg.T >= qs->n_lanes) cfg.L = std::min((int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64), cfg.T);
+    if (tma) {
+        /* the 128-byte row of the tensor map lies inside every tile */
+        cfg.row_lanes = fp32 ? 4 : 3;
+        cfg.max_groups = QGB_MAX_GROUPS;
+        cfg.L = std::max(cfg.L, cfg.row_lanes);
+    }
+    int want_ctas_tma = 3;
     cfg.max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, QGB_MAX_OPS));
+    if (tma) cfg.max_ops = std::min(cfg.max_ops, tma_ops);
     {
         /* stages: each costs a per-thread table entry in shared memory; keep the CTA small enough
-         * for the occupancy its launch bounds ask for (3 / 2 / 1 CTAs per SM) */
+         * for the occupancy its launch bounds ask for */
         const int nthr = 1 << (cfg.T - cfg.K);
-        int want_ctas = nthr <= 256 ? (n_buf == 2 ? 3 : 4) : (nthr <= 512 ? 2 : 1);
+        int want_ctas;
+        if (tma)
+            want_ctas = nthr <= 256 ? (n_buf == 3 ? 2 : 3) : 1;
+        if (tma && g.opt.ctas_per_sm > 0) want_ctas_tma = (int)g.opt.ctas_per_sm;
+        else
+            want_ctas = nthr <= 256 ? (n_buf == 2 ? 3 : 4) : (nthr <= 512 ? 2 : 1);
         if (g.opt.ctas_per_sm > 0) want_ctas = (int)g.opt.ctas_per_sm;
         const size_t budget = (size_t)(g.max_smem_optin + 1024) / want_ctas - 1024;
         int ms = QGB_MAX_STAGES;
-        while (ms > 2 && tile_pass_smem_bytes(qs->prec, cfg.T, cfg.L, ms, n_buf) > budget) --ms;
+        while (ms > 2 && smem_bytes(cfg.T, cfg.L, ms) > budget) --ms;
         cfg.max_stages = ms;
     }
     cfg.max_cost = (int)g.opt.max_cost;
@@ -303,7 +325,12 @@ void flush_tiled(QStates *qs) {
     while (!qs->queue.empty()) {
         plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
         if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
-        CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, n_buf, g.stream));
+        if (tma && prog.n_groups >= 1) {
+            CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, want_ctas_tma, g.stream));
+            g.stats.tma_passes += 1;
+        } else {
+            CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, tma ? 1 : n_buf, g.stream));
+        }
         g.stats.kernel_launches += 1;
         g.stats.tile_passes += 1;
         g.stats.gates_executed += st.gates_in_pass;
@@ -478,6 +505,7 @@ int qgb_devices_initialize(const int *device_ids, int n_device_ids, int max_po2i
     CUDA_CHECK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
     CUDA_CHECK(tile_pass_configure(g.max_smem_optin, g.sm_count));
+    CUDA_CHECK(tma_pass_configure(g.max_smem_optin, g.sm_count));
     g.pool.budget = memory_store_size;
     CUDA_CHECK(cudaMalloc(&g.d_partials, sizeof(double) * 4096));
     CUDA_CHECK(cudaMallocHost(&g.h_scalar, sizeof(double) * 16));
@@ -745,34 +773,78 @@ int qgb_qstates_flip(qgb_handle h) {
     QGB_CATCH
 }
 
+/* CUDA IPC.  The handle names the whole driver allocation a pointer lives in (small cudaMalloc
+ * blocks may share one), so the export also reports the pointer's offset inside it, and a
+ * handle is mapped once per process however many qstates refer to it (reference counted). */
+namespace {
+typedef int (*GetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);
+struct IpcMapping {
+    void *base;
+    int refs;
+};
+std::map<std::string, IpcMapping> g_ipc_open;
+} // namespace
+
 int qgb_qstates_ipc_export(qgb_handle h, void *handle64, int64_t *offset) {
     QGB_TRY
     require_init();
     QStates *qs = QS(h);
     check_allocated(qs);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *base = qs->d_amp;
+    static GetAddressRangeFn get_range = nullptr;
+    if (!get_range) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            get_range = reinterpret_cast<GetAddressRangeFn>(fn);
+        cudaGetLastError();
+    }
+    if (get_range) {
+        unsigned long long b = 0;
+        size_t size = 0;
+        if (get_range(&b, &size, reinterpret_cast<unsigned long long>(qs->d_amp)) == 0 && b) base = reinterpret_cast<void *>(b);
+    }
     cudaIpcMemHandle_t hd;
-    CUDA_CHECK(cudaIpcGetMemHandle(&hd, qs->d_amp)); /* every pool block is its own cudaMalloc */
+    CUDA_CHECK(cudaIpcGetMemHandle(&hd, base));
     std::memcpy(handle64, &hd, sizeof(hd));
-    if (offset) *offset = 0;
+    if (offset) *offset = (int64_t)(reinterpret_cast<char *>(qs->d_amp) - reinterpret_cast<char *>(base));
     QGB_CATCH
 }
 
 int qgb_ipc_open(const void *handle64, uint64_t *base_ptr) {
     QGB_TRY
     require_init();
-    cudaIpcMemHandle_t hd;
-    std::memcpy(&hd, handle64, sizeof(hd));
-    void *p = nullptr;
-    CUDA_CHECK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
-    *base_ptr = reinterpret_cast<uint64_t>(p);
+    const std::string key(reinterpret_cast<const char *>(handle64), 64);
+    auto it = g_ipc_open.find(key);
+    if (it != g_ipc_open.end()) {
+        it->second.refs += 1;
+        *base_ptr = reinterpret_cast<uint64_t>(it->second.base);
+    } else {
+        cudaIpcMemHandle_t hd;
+        std::memcpy(&hd, handle64, sizeof(hd));
+        void *p = nullptr;
+        CUDA_CHECK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+        g_ipc_open[key] = IpcMapping{p, 1};
+        *base_ptr = reinterpret_cast<uint64_t>(p);
+    }
     QGB_CATCH
 }
 
 int qgb_ipc_close(uint64_t base_ptr) {
     QGB_TRY
     require_init();
-    CUDA_CHECK(cudaIpcCloseMemHandle(reinterpret_cast<void *>(base_ptr)));
+    for (auto it = g_ipc_open.begin(); it != g_ipc_open.end(); ++it) {
+        if (reinterpret_cast<uint64_t>(it->second.base) != base_ptr) continue;
+        if (--it->second.refs == 0) {
+            CUDA_CHECK(cudaStreamSynchronize(g.stream)); /* no kernel may still use the mapping */
+            void *p = it->second.base;
+            g_ipc_open.erase(it);
+            CUDA_CHECK(cudaIpcCloseMemHandle(p));
+        }
+        break;
+    }
     QGB_CATCH
 }
 
@@ -1203,6 +1275,8 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "queue_limit") g.opt.queue_limit = value;
     else if (k == "tile_buffers") g.opt.tile_buffers = value;
     else if (k == "ctas_per_sm") g.opt.ctas_per_sm = value;
+    else if (k == "tma") g.opt.tma = value;
+    else if (k == "tma_buffers") g.opt.tma_buffers = value;
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH
 }

@@ -41,6 +41,15 @@ cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, int n_buf
 size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages, int n_buf);
 cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
 
+/* the same pass with TMA tensor-map staging (kernels_tma.cu); needs prog.n_groups >= 1;
+ * n_buf = 2 or 3 tile buffers per CTA; min_ctas = resident CTAs per SM the register budget is
+ * set for (3: 80 registers per thread, 2: up to 128) */
+template <typename real>
+cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf, int min_ctas, cudaStream_t stream);
+/* shared memory of one CTA: n_buf tiles, the matrices of n_ops ops, n_stages thread tables */
+size_t tma_pass_smem_bytes(int prec, int T, int n_stages, int n_buf, int n_ops);
+cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);
+
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
                                uint64_t ctrl_mask, uint64_t zero_mask, cudaStream_t stream);
 

@@ -1,0 +1,498 @@
+/*
+ * kernels_tma.cu — the fused gate pass with TMA staging (sm_100a).
+ *
+ *   tma_pass_kernel   same pass program and op bodies as tile_pass_kernel (kernels_tile.cu),
+ *                     but a tile travels HBM -> shared memory -> HBM as ONE tensor-map copy
+ *                     each way (cp.async.bulk.tensor, UTMALDG / UTMASTG), issued by one
+ *                     thread and tracked by mbarriers / bulk groups.  The per-thread address
+ *                     arithmetic of the cp.async version (about a third of its instruction
+ *                     stream, profiles/r1g_tile_pass.md) disappears, and a ring of NBUF tile
+ *                     buffers keeps a load, the gate stages and a store in flight at once.
+ *
+ * The tile is the sub-cube of T tile lanes (program.h).  The state vector is described to the
+ * TMA unit as a 5-dimensional tensor: dimension 0 is one 128-byte row (the low row_lanes
+ * lanes), dimensions 1..4 are the planner's lane groups [tile lanes][other lanes]
+ * (PassProgram::grp_*): the box takes the tile lanes of every group, the tile number supplies
+ * the coordinates of the other lanes.  CU_TENSOR_MAP_SWIZZLE_128B gives exactly the
+ * bank-conflict-free layout the stage code expects (program.h: tile_swizzle).
+ *
+ * Reference semantics: qgate/simulator/src/CPUQubitProcessor.cpp:307-362; the incumbent device
+ * code is DeviceProcPrimitives.cu:198-249 (one launch and one state sweep per gate).
+ */
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "tile_ops.cuh"
+
+namespace qgb {
+
+namespace {
+
+struct TmaGeometry {
+    int32_t n_groups;
+    int32_t shift[QGB_MAX_GROUPS];   /* first tile-number bit consumed by the group            */
+    uint32_t mask[QGB_MAX_GROUPS];   /* (1 << grp_r) - 1                                       */
+    int32_t tbits[QGB_MAX_GROUPS];   /* coordinate = rest bits << tbits                        */
+    int32_t base_shift[QGB_MAX_GROUPS]; /* lane of the group's first non-tile lane            */
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, const void *src, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];\n" ::"l"(map),
+                 "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+/* ---- op bodies of this kernel ----------------------------------------------------------
+ * One specialised body per Op::code, entered through a switch on a CTA-uniform value.  The 2x2
+ * matrices of the pass live in shared memory (copied there once per CTA): a body fetches its
+ * matrix with 128-bit shared loads through a pointer that may differ per thread (gate
+ * multiplexed by a thread bit), so there is no per-thread select of 8 values; thread-bit
+ * controls are a branch around the body (a thread either runs it or skips it, nothing else
+ * diverges); register-bit controls and register-bit multiplexers are resolved at compile
+ * time or by uniform tests.  Arithmetic: CPUQubitProcessor.cpp:307-362. */
+
+template <typename real> struct Mat8;
+template <> struct Mat8<double> {
+    double v[8];
+    __device__ __forceinline__ void load(const double *p) {
+        const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double2 t = q[i];
+            v[2 * i] = t.x;
+            v[2 * i + 1] = t.y;
+        }
+    }
+};
+template <> struct Mat8<float> {
+    float v[8];
+    __device__ __forceinline__ void load(const float *p) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float4 t = q[i];
+            v[4 * i] = t.x;
+            v[4 * i + 1] = t.y;
+            v[4 * i + 2] = t.z;
+            v[4 * i + 3] = t.w;
+        }
+    }
+};
+
+template <typename real>
+__device__ __forceinline__ void pair_2x2(typename Cplx<real>::type &x0, typename Cplx<real>::type &x1,
+                                         const real (&m)[8]) {
+    const real q0r = x0.x, q0i = x0.y, q1r = x1.x, q1i = x1.y;
+    x0.x = m[0] * q0r - m[1] * q0i + m[2] * q1r - m[3] * q1i;
+    x0.y = m[0] * q0i + m[1] * q0r + m[2] * q1i + m[3] * q1r;
+    x1.x = m[4] * q0r - m[5] * q0i + m[6] * q1r - m[7] * q1i;
+    x1.y = m[4] * q0i + m[5] * q0r + m[6] * q1i + m[7] * q1r;
+}
+
+/* MODE 0: every pair; 1: pairs allowed by regmask (uniform); 2 / 3: pairs whose register bit J2 is
+ * 0 / 1 (compile time) */
+template <typename real, int K, int J, int MODE, int J2>
+__device__ __forceinline__ void lean_gen(typename Cplx<real>::type (&a)[1 << K], const real *mats, uint32_t regmask) {
+    Mat8<real> m;
+    m.load(mats);
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        if (MODE == 2 && (r0 & (1 << J2))) continue;
+        if (MODE == 3 && !(r0 & (1 << J2))) continue;
+        if (MODE == 1 && !(regmask & (1u << r0))) continue;
+        pair_2x2<real>(a[r0], a[r0 | (1 << J)], m.v);
+    }
+}
+
+template <typename real, int K, int J, int J2>
+__device__ __forceinline__ void lean_regmux(typename Cplx<real>::type (&a)[1 << K], const real *mats) {
+    if (J == J2) return; /* never planned */
+    lean_gen<real, K, J, 2, (J == J2 ? 0 : J2)>(a, mats, 0u);
+    lean_gen<real, K, J, 3, (J == J2 ? 0 : J2)>(a, mats + 8, 0u);
+}
+
+template <typename real, int K, int J>
+__device__ __forceinline__ void lean_swap(typename Cplx<real>::type (&a)[1 << K], uint32_t regmask) {
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        if (regmask & (1u << r0)) {
+            const typename Cplx<real>::type t = a[r0];
+            a[r0] = a[r0 | (1 << J)];
+            a[r0 | (1 << J)] = t;
+        }
+    }
+}
+
+#define QGB_J(j) ((j) < K ? (j) : 0)
+
+/* One op on the registers of a thread that takes part in it (`mm` = the op's matrix or factor
+ * already selected for this thread and tile, `mo` = the op's [m | m1] block). */
+template <typename real, int K>
+__device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
+                                              const real *mo, const real *mm) {
+    switch (op.code) {
+    case OPC_GEN(0): lean_gen<real, K, 0, 0, 0>(a, mm, 0u); break;
+    case OPC_GEN(1): lean_gen<real, K, QGB_J(1), 0, 0>(a, mm, 0u); break;
+    case OPC_GEN(2): lean_gen<real, K, QGB_J(2), 0, 0>(a, mm, 0u); break;
+    case OPC_GEN(3): if (K > 3) lean_gen<real, K, QGB_J(3), 0, 0>(a, mm, 0u); break;
+    case OPC_GEN_MASKED(0): lean_gen<real, K, 0, 1, 0>(a, mm, op.regmask); break;
+    case OPC_GEN_MASKED(1): lean_gen<real, K, QGB_J(1), 1, 0>(a, mm, op.regmask); break;
+    case OPC_GEN_MASKED(2): lean_gen<real, K, QGB_J(2), 1, 0>(a, mm, op.regmask); break;
+    case OPC_GEN_MASKED(3): if (K > 3) lean_gen<real, K, QGB_J(3), 1, 0>(a, mm, op.regmask); break;
+    case OPC_GEN_REGMUX(0, 1): lean_regmux<real, K, 0, QGB_J(1)>(a, mo); break;
+    case OPC_GEN_REGMUX(0, 2): lean_regmux<real, K, 0, QGB_J(2)>(a, mo); break;
+    case OPC_GEN_REGMUX(0, 3): if (K > 3) lean_regmux<real, K, 0, QGB_J(3)>(a, mo); break;
+    case OPC_GEN_REGMUX(1, 0): lean_regmux<real, K, QGB_J(1), 0>(a, mo); break;
+    case OPC_GEN_REGMUX(1, 2): lean_regmux<real, K, QGB_J(1), QGB_J(2)>(a, mo); break;
+    case OPC_GEN_REGMUX(1, 3): if (K > 3) lean_regmux<real, K, QGB_J(1), QGB_J(3)>(a, mo); break;
+    case OPC_GEN_REGMUX(2, 0): lean_regmux<real, K, QGB_J(2), 0>(a, mo); break;
+    case OPC_GEN_REGMUX(2, 1): lean_regmux<real, K, QGB_J(2), QGB_J(1)>(a, mo); break;
+    case OPC_GEN_REGMUX(2, 3): if (K > 3) lean_regmux<real, K, QGB_J(2), QGB_J(3)>(a, mo); break;
+    case OPC_GEN_REGMUX(3, 0): if (K > 3) lean_regmux<real, K, QGB_J(3), 0>(a, mo); break;
+    case OPC_GEN_REGMUX(3, 1): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(1)>(a, mo); break;
+    case OPC_GEN_REGMUX(3, 2): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(2)>(a, mo); break;
+    case OPC_SWAP(0): lean_swap<real, K, 0>(a, op.regmask); break;
+    case OPC_SWAP(1): lean_swap<real, K, QGB_J(1)>(a, op.regmask); break;
+    case OPC_SWAP(2): lean_swap<real, K, QGB_J(2)>(a, op.regmask); break;
+    case OPC_SWAP(3): if (K > 3) lean_swap<real, K, QGB_J(3)>(a, op.regmask); break;
+    case OPC_DIAG_REG: {
+        const uint32_t regmask = op.regmask, regsel = op.regsel;
+        apply_phase<real, K>(a, mo[0], mo[1], regmask & ~regsel);
+        apply_phase<real, K>(a, mo[2], mo[3], regmask & regsel);
+        break;
+    }
+    case OPC_DIAG_THR: apply_phase<real, K>(a, mm[0], mm[1], op.regmask); break;
+    default: break;
+    }
+}
+
+/* Shared memory: [NBUF tiles, 1024-byte aligned][NBUF mbarriers][per stage, per thread: base slot] */
+template <typename real, int K, int NT, int MINB, int NBUF>
+__global__ void __launch_bounds__(NT, MINB)
+tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_constant__ CUtensorMap tmap,
+                const __grid_constant__ TmaGeometry geo) {
+    typedef typename Cplx<real>::type cplx;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int T = prog.T;
+    const uint32_t tile_bytes = (uint32_t)sizeof(cplx) << T;
+    /* SWIZZLE_128B needs 1024-byte aligned tile buffers */
+    unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *full = reinterpret_cast<uint64_t *>(tiles + NBUF * tile_bytes);
+    real *mats = reinterpret_cast<real *>(full + NBUF + (NBUF & 1)); /* 16-byte aligned: [op][m, m1][8] */
+    uint32_t *lut = reinterpret_cast<uint32_t *>(mats + 16 * prog.n_ops);
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
+
+    /* the pass's matrices, once per CTA */
+    for (int i = tid; i < 16 * prog.n_ops; i += nthr) {
+        const Op<real> &op = prog.op[i >> 4];
+        mats[i] = (i & 8) ? op.m1[i & 7] : op.m[i & 7];
+    }
+
+    /* per stage: byte offset (inside a tile buffer) of this thread's base element */
+    for (int s = 0; s < prog.n_stages; ++s) {
+        const Stage &st = prog.stage[s];
+        uint32_t ebase = 0;
+        for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
+        /* low 16 bits: element index (op predicates), high bits: swizzled byte offset / 8 */
+        lut[s * nthr + tid] = ebase | ((swz<real>(ebase) * (uint32_t)sizeof(cplx) / 8u) << 16);
+    }
+    /* Which ops this thread takes part in (thread-bit controls) and where it takes the second
+     * matrix / factor (multiplexer or diagonal target on a thread bit): one bit per op, fixed
+     * for the whole pass because a thread's elements do not depend on the tile. */
+    uint32_t act = 0, sel_thr = 0; /* n_ops <= 32 */
+    for (int s = 0; s < prog.n_stages; ++s) {
+        const Stage &st = prog.stage[s];
+        uint32_t ebase = 0;
+        for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
+        for (int o = st.op_begin; o < st.op_end; ++o) {
+            const Op<real> &op = prog.op[o];
+            if ((ebase & op.cmt) == op.cmt) act |= 1u << o;
+            if (ebase & op.tsel) sel_thr |= 1u << o;
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint64_t n_tiles = 1ull << (prog.n_lanes - T);
+    const uint64_t stride = gridDim.x;
+
+    /* tile number -> tensor coordinates of the tile's origin */
+    auto issue_load = [&](uint64_t t, int b) {
+        int c[QGB_MAX_GROUPS];
+#pragma unroll
+        for (int d = 0; d < QGB_MAX_GROUPS; ++d)
+            c[d] = (int)((((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.tbits[d]);
+        mbar_expect_tx(&full[b], tile_bytes);
+        tma_load_5d(tiles + (size_t)b * tile_bytes, &tmap, &full[b], c[0], c[1], c[2], c[3]);
+    };
+    auto issue_store = [&](uint64_t t, int b) {
+        int c[QGB_MAX_GROUPS];
+#pragma unroll
+        for (int d = 0; d < QGB_MAX_GROUPS; ++d)
+            c[d] = (int)((((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.tbits[d]);
+        tma_store_5d(&tmap, tiles + (size_t)b * tile_bytes, c[0], c[1], c[2], c[3]);
+        bulk_commit();
+    };
+
+    /* prologue: the first tile */
+    if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+
+    int b = 0;            /* buffer of the tile being worked on */
+    uint32_t parity = 0;  /* phase of full[b] this tile completes */
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += stride) {
+        /* prefetch the next tile into buffer b + 1.  That buffer held the tile stored NBUF - 1
+         * iterations ago, so at most the newest NBUF - 2 stores may still be reading shared
+         * memory (NBUF == 2: wait for the store just issued; NBUF == 3: load, stages and store
+         * of three consecutive tiles overlap without a wait) */
+        if (tid == 0) {
+            const uint64_t tn = t + stride;
+            if (tn < n_tiles) {
+                bulk_wait_read<NBUF - 2>();
+                issue_load(tn, b + 1 == NBUF ? 0 : b + 1);
+            }
+        }
+        /* index of the tile's origin -> the ops this tile skips (controls outside the tile) and
+         * the ops that take their second matrix / factor (multiplexer or diagonal target
+         * outside the tile): CTA-uniform bit masks over the ops */
+        uint64_t base = 0;
+#pragma unroll
+        for (int d = 0; d < QGB_MAX_GROUPS; ++d)
+            base |= (uint64_t)(((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.base_shift[d];
+        uint32_t eff = act, sel = sel_thr;
+        for (int i = 0; i < prog.n_out; ++i) {
+            const uint64_t cm = prog.out[i].ctrl_mask;
+            const int o = prog.out[i].op, lane = prog.out[i].sel_lane;
+            if ((base & cm) != cm) eff &= ~(1u << o);
+            if (lane >= 0 && ((base >> lane) & 1ull)) sel |= 1u << o;
+        }
+
+        mbar_wait(&full[b], parity);
+        unsigned char *buf = tiles + (size_t)b * tile_bytes;
+
+        for (int s = 0; s < prog.n_stages; ++s) {
+            const Stage &st = prog.stage[s];
+            if (st.op_begin == st.op_end) continue;
+            const uint32_t packed = lut[s * nthr + tid];
+            const uint32_t sbyte = (packed >> 16) << 3;
+
+            /* slot of register r: base slot ^ XOR of the per-bit constants over the bits of r */
+            uint32_t off[1 << K];
+            off[0] = sbyte;
+#pragma unroll
+            for (int r = 1; r < (1 << K); ++r) {
+                const int low = r & -r; /* lowest set bit */
+                const int j = low == 1 ? 0 : (low == 2 ? 1 : (low == 4 ? 2 : 3));
+                off[r] = off[r ^ low] ^ st.xb[j];
+            }
+            cplx a[1 << K];
+#pragma unroll
+            for (int r = 0; r < (1 << K); ++r) a[r] = *reinterpret_cast<const cplx *>(buf + off[r]);
+
+            {
+                uint32_t bit = 1u << st.op_begin;
+                const real *mo = mats + 16 * st.op_begin;
+                for (int o = st.op_begin; o < st.op_end; ++o, bit <<= 1, mo += 16) {
+                    if (!(eff & bit)) continue;
+                    lean_apply_op<real, K>(a, prog.op[o], mo, mo + ((sel & bit) ? 8 : 0));
+                }
+            }
+
+#pragma unroll
+            for (int r = 0; r < (1 << K); ++r) *reinterpret_cast<cplx *>(buf + off[r]) = a[r];
+            if (s + 1 < prog.n_stages) __syncthreads();
+        }
+        /* generic-proxy writes -> visible to the async proxy, then one thread stores the tile */
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) issue_store(t, b);
+
+        if (++b == NBUF) {
+            b = 0;
+            parity ^= 1u;
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode = nullptr;
+int g_tma_sm_count = 148;
+int g_tma_max_smem = 48 * 1024;
+
+cudaError_t resolve_encode() {
+    if (g_encode) return cudaSuccess;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t rc = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (rc != cudaSuccess) return rc;
+    if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return cudaSuccess;
+}
+
+template <typename real>
+cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *map, TmaGeometry *geo) {
+    const uint64_t elem = 2 * sizeof(real);            /* bytes of one amplitude */
+    const uint64_t scalars_per_row = 128 / sizeof(real); /* tensor elements are scalars (re, im separate) */
+    cuuint64_t gdim[5];
+    cuuint64_t gstride[4];
+    cuuint32_t box[5], estride[5] = {1, 1, 1, 1, 1};
+    gdim[0] = scalars_per_row;
+    box[0] = (cuuint32_t)scalars_per_row;
+    const uint64_t total_bytes = elem << prog.n_lanes;
+    int consumed = 0;
+    geo->n_groups = prog.n_groups;
+    for (int d = 0; d < QGB_MAX_GROUPS; ++d) {
+        if (d < prog.n_groups) {
+            const int s = prog.grp_start[d], t = prog.grp_t[d], r = prog.grp_r[d];
+            gdim[d + 1] = 1ull << (t + r);
+            box[d + 1] = 1u << t;
+            gstride[d] = elem << s;
+            geo->shift[d] = consumed;
+            geo->mask[d] = r >= 32 ? 0xffffffffu : ((1u << r) - 1u);
+            geo->tbits[d] = t;
+            geo->base_shift[d] = s + t;
+            consumed += r;
+        } else {
+            /* padding dimension of extent 1 (keeps one rank-5 instruction for every tile shape) */
+            gdim[d + 1] = 1;
+            box[d + 1] = 1;
+            gstride[d] = total_bytes < (1ull << 39) ? (total_bytes >= 128 ? total_bytes : 128) : (1ull << 39);
+            geo->shift[d] = 0;
+            geo->mask[d] = 0;
+            geo->tbits[d] = 0;
+            geo->base_shift[d] = 0;
+        }
+    }
+    if (consumed != prog.n_lanes - prog.T) return cudaErrorInvalidValue;
+    const CUtensorMapDataType dt = sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult res = g_encode(map, dt, 5, amp, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <typename real, int K, int NT, int MINB, int NBUF>
+cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
+                               size_t smem, cudaStream_t stream) {
+    static int configured = 0;
+    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF>;
+    if (!configured) {
+        cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_max_smem);
+        if (rc != cudaSuccess) return rc;
+        configured = 1;
+    }
+    const unsigned nthr = 1u << (prog.T - K);
+    int per_sm = 0;
+    cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)nthr, smem);
+    if (rc != cudaSuccess) return rc;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const uint64_t n_tiles = 1ull << (prog.n_lanes - prog.T);
+    const uint64_t resident = (uint64_t)g_tma_sm_count * per_sm; /* persistent: one wave */
+    const unsigned nblocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    kernel<<<nblocks, nthr, smem, stream>>>(prog, map, geo);
+    return cudaGetLastError();
+}
+
+template <typename real, int K>
+cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int prec, int n_buf, int min_ctas,
+                                cudaStream_t stream) {
+    cudaError_t rc = resolve_encode();
+    if (rc != cudaSuccess) return rc;
+    CUtensorMap map;
+    TmaGeometry geo;
+    rc = encode_map<real>(prog, amp, &map, &geo);
+    if (rc != cudaSuccess) return rc;
+    const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.n_stages, n_buf, prog.n_ops);
+    const int nthr = 1 << (prog.T - prog.K);
+    if (n_buf >= 3) {
+        if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 3>(prog, map, geo, smem, stream);
+        if (nthr <= 512) return launch_tma_variant<real, K, 512, 1, 3>(prog, map, geo, smem, stream);
+        return launch_tma_variant<real, K, 1024, 1, 3>(prog, map, geo, smem, stream);
+    }
+    if (nthr <= 256 && min_ctas >= 3) return launch_tma_variant<real, K, 256, 3, 2>(prog, map, geo, smem, stream);
+    if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 2>(prog, map, geo, smem, stream);
+    if (nthr <= 512) return launch_tma_variant<real, K, 512, 1, 2>(prog, map, geo, smem, stream);
+    return launch_tma_variant<real, K, 1024, 1, 2>(prog, map, geo, smem, stream);
+}
+
+} // namespace
+
+size_t tma_pass_smem_bytes(int prec, int T, int n_stages, int n_buf, int n_ops) {
+    const size_t elem = prec == 1 ? 16 : 8;
+    const int K = prec == 1 ? QGB_K64 : QGB_K32;
+    size_t tiles = n_buf * (elem << T);
+    tiles = (tiles + 1023) & ~(size_t)1023;
+    /* + mbarriers, the matrices of up to QGB_MAX_OPS ops, the per-stage thread table, alignment slack */
+    return tiles + 8 * (n_buf + 1) + 8 * elem * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
+}
+
+cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
+    if (sm_count > 0) g_tma_sm_count = sm_count;
+    g_tma_max_smem = max_smem_optin;
+    return cudaSuccess;
+}
+
+template <>
+cudaError_t launch_tma_pass<double>(const PassProgram<double> &prog, void *amp, int n_buf, int min_ctas,
+                                    cudaStream_t stream) {
+    if (prog.K != QGB_K64 || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
+        return cudaErrorInvalidValue;
+    return launch_tma_by_shape<double, QGB_K64>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream);
+}
+
+template <>
+cudaError_t launch_tma_pass<float>(const PassProgram<float> &prog, void *amp, int n_buf, int min_ctas,
+                                   cudaStream_t stream) {
+    if (prog.K != QGB_K32 || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
+        return cudaErrorInvalidValue;
+    return launch_tma_by_shape<float, QGB_K32>(prog, amp, 2, n_buf >= 3 ? 3 : 2, min_ctas, stream);
+}
+
+} // namespace qgb

@@ -162,6 +162,12 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
 
     uint64_t S = (T >= n) ? all_lanes : ((1ull << L) - 1);
     int count = popcount64(S);
+    /* TMA staging: the tile must stay describable by a 5-dimensional tensor map */
+    auto fits_tensor_map = [&](uint64_t lanes) {
+        if (cfg.max_groups <= 0) return true;
+        int8_t gs[QGB_MAX_GROUPS], gt[QGB_MAX_GROUPS], gr[QGB_MAX_GROUPS];
+        return tile_groups(lanes, n, cfg.row_lanes, gs, gt, gr) <= std::min(cfg.max_groups, QGB_MAX_GROUPS);
+    };
     uint64_t blockedX = 0, blockedZ = 0;
     std::vector<Picked> picked;
     std::vector<uint64_t> stageR; /* lane masks of the register bits of each stage */
@@ -182,7 +188,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             blocked = true;
         bool add_lane = false;
         if (!blocked && xq && !(S & xq)) {
-            if (count < T)
+            if (count < T && fits_tensor_map(S | xq))
                 add_lane = true;
             else
                 blocked = true;
@@ -221,17 +227,26 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
 
     /* fill the tile with the highest unused lanes when fewer than T were needed (keeps the
      * kernel shape fixed; any lane works because unused tile lanes are just carried). */
-    for (int lane = n - 1; lane >= 0 && count < T; --lane)
-        if (!(S & (1ull << lane))) {
-            S |= 1ull << lane;
-            ++count;
-        }
+    while (count < T) {
+        int lane = n - 1;
+        /* (a lane next to an existing run never adds a group, so there is always a candidate) */
+        while (lane >= 0 && ((S & (1ull << lane)) || !fits_tensor_map(S | (1ull << lane)))) --lane;
+        if (lane < 0) break;
+        S |= 1ull << lane;
+        ++count;
+    }
 
     std::memset(&prog, 0, sizeof(prog));
     prog.n_lanes = n;
     prog.T = T;
     prog.L = L;
     prog.K = K;
+    prog.row_lanes = cfg.row_lanes;
+    prog.n_groups = 0;
+    if (cfg.max_groups > 0 && count == T && ((S & ((1ull << cfg.row_lanes) - 1)) == (1ull << cfg.row_lanes) - 1)) {
+        const int ng = tile_groups(S, n, cfg.row_lanes, prog.grp_start, prog.grp_t, prog.grp_r);
+        prog.n_groups = ng <= QGB_MAX_GROUPS ? ng : 0;
+    }
     int lane_to_tile[64];
     {
         int p = 0, r = 0;
@@ -273,6 +288,8 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 if (r & (1 << jj)) roff |= 1u << st.R[jj];
             st.sro[r] = (uint16_t)tile_swizzle(roff, cfg.fp32);
         }
+        for (int jj = 0; jj < QGB_MAX_REG_BITS; ++jj)
+            st.xb[jj] = jj < K ? tile_swizzle(1u << st.R[jj], cfg.fp32) * (uint32_t)(2 * sizeof(real)) : 0u;
         st.op_begin = st.op_end = 0;
     }
 
@@ -304,7 +321,8 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         op.regsel = 0;
         op.bit = 0;
         op.mux_out = 0;
-        op.pad_ = 0;
+        op.code = 0;
+        int mux_regbit = -1;
         if (gate_is_diag(g)) {
             const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
@@ -351,6 +369,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 const int j = regbit(g.mux);
                 if (j >= 0) {
                     mux_arm = ARM_MUX_REG;
+                    mux_regbit = j;
                     for (int r = 0; r < (1 << K); ++r)
                         if (r & (1 << j)) op.regsel |= 1u << r;
                 } else {
@@ -378,6 +397,32 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             for (int j = 0; j < K; ++j)
                 if (r & (1 << j)) roff |= 1u << st.R[j];
             if ((roff & ct & rmask) == (ct & rmask)) op.regmask |= 1u << r;
+        }
+        const uint32_t all_regs = (1u << K) >= 32 ? 0xffffffffu : ((1u << (1 << K)) - 1u);
+        if (op.kind == OP_GEN) {
+            if (mux_regbit >= 0)
+                op.code = OPC_GEN_REGMUX(op.bit, mux_regbit);
+            else
+                op.code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
+        } else if (op.kind == OP_SWAP) {
+            op.code = OPC_SWAP(op.bit);
+        } else {
+            op.code = op.regsel ? OPC_DIAG_REG : OPC_DIAG_THR;
+            /* selected factor at the same place as a multiplexed matrix: m = d0.., m1 = d1.. */
+            op.m1[0] = op.m[2];
+            op.m1[1] = op.m[3];
+        }
+        {
+            int sel_lane = -1;
+            if (mux_arm == ARM_MUX_OUT) sel_lane = op.mux_out;
+            if (op.kind == OP_DIAG_OUT) sel_lane = op.bit;
+            if (op.ctrl_out != 0 || sel_lane >= 0) {
+                auto &ref = prog.out[prog.n_out++];
+                ref.ctrl_mask = op.ctrl_out;
+                ref.op = (int16_t)(n_ops - 1);
+                ref.sel_lane = (int16_t)sel_lane;
+                ref.pad_ = 0;
+            }
         }
     }
     if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;

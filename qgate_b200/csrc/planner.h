@@ -18,6 +18,10 @@ struct PlanConfig {
     int lookahead = 4096; /* how far past the first blocked gate the planner searches      */
     bool fp32 = false;    /* selects the shared-memory bank classes used to order W[]      */
     int max_cost = 1 << 30; /* cap on the summed op cost of a pass (see op_cost)            */
+    /* TMA staging: lanes of one 128-byte shared-memory row (3 complex128 / 4 complex64) and the
+     * most tensor-map groups a tile may need (0: any tile shape, cp.async staging) */
+    int row_lanes = 0;
+    int max_groups = 0;
 };
 
 struct PlanStats {

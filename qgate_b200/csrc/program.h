@@ -43,6 +43,7 @@ enum OpKind : int {
 #define QGB_MAX_LANES 40
 #define QGB_MAX_STAGES 40
 #define QGB_MAX_OPS 112
+#define QGB_MAX_GROUPS 4    /* tensor-map dimensions above the 128-byte row (TMA staging)    */
 
 /* One op of a stage.  The control predicate of an amplitude with tile index e = ebase | roff(r)
  * (thread part | register part) is split on the host: `cmt` is tested once per thread,
@@ -66,8 +67,17 @@ struct Op {
     real m1[8];           /* multiplexed OP_GEN: the matrix where the multiplexer bit is 1 */
                           /* (ARM_MUX_OUT: `mux_out` = the state-vector lane, outside tile) */
     int32_t mux_out;
-    int32_t pad_;
+    int32_t code;         /* OPC_*: the specialised body kernels_tma.cu runs for this op          */
 };
+
+/* Op::code — one value per specialised op body of the TMA-staged kernel (switch on a uniform) */
+#define OPC_GEN(j) (0 + (j))                      /* 2x2 on register bit j; matrix = m, or m1 where a  */
+                                                  /* thread-bit / outside-tile multiplexer is 1        */
+#define OPC_GEN_MASKED(j) (4 + (j))               /* the same under register-bit controls (regmask)    */
+#define OPC_GEN_REGMUX(j, j2) (8 + 4 * (j) + (j2)) /* multiplexed by register bit j2: m / m1 per pair  */
+#define OPC_SWAP(j) (24 + (j))
+#define OPC_DIAG_REG 28
+#define OPC_DIAG_THR 29
 
 /* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
  * (byte address bits [6:4] ^= bits [9:7]).  Linear over GF(2), so
@@ -84,6 +94,8 @@ struct Stage {
     int8_t R[QGB_MAX_REG_BITS];           /* register bit j  <-> tile bit R[j], ascending   */
     int8_t W[QGB_MAX_TILE_LANES];         /* thread bit i    <-> tile bit W[i]              */
     uint16_t sro[1 << QGB_MAX_REG_BITS];  /* swizzled tile offset of register index r       */
+    uint32_t xb[QGB_MAX_REG_BITS];        /* swizzled BYTE offset of register bit j: the slot of */
+                                          /* register r is base ^ XOR of xb[j] over the bits of r */
 };
 
 template <typename real>
@@ -96,9 +108,60 @@ struct PassProgram {
     int32_t n_ops;
     int8_t tile_lane[QGB_MAX_TILE_LANES];   /* tile bit p <-> lane, ascending, [p] = p for p < L */
     int8_t rest_lane[QGB_MAX_LANES];        /* the n_lanes - T other lanes, ascending        */
+    /* TMA staging (kernels_tma.cu): the lanes above the 128-byte row (row_lanes of them) are cut,
+     * ascending, into groups of [grp_t tile lanes][grp_r other lanes] starting at lane grp_start;
+     * group d is dimension d + 1 of the pass's tensor map (box 2^grp_t of 2^(grp_t + grp_r)).
+     * n_groups == 0: the tile shape does not fit a tensor map (cp.async staging only). */
+    int32_t row_lanes;
+    int32_t n_groups;
+    int8_t grp_start[QGB_MAX_GROUPS], grp_t[QGB_MAX_GROUPS], grp_r[QGB_MAX_GROUPS];
+    /* ops that look at lanes OUTSIDE the tile (controls, multiplexer, diagonal target): the
+     * TMA-staged kernel turns them into two per-tile bit masks over the ops instead of testing
+     * every op of every tile (needs n_ops <= 32) */
+    int32_t n_out;
+    struct OutRef {
+        uint64_t ctrl_mask;   /* the op runs only in tiles whose origin has these bits set       */
+        int16_t op;           /* op index                                                       */
+        int16_t sel_lane;     /* >= 0: the op takes m1 / d1 in tiles whose origin has this bit  */
+        int32_t pad_;
+    } out[QGB_MAX_OPS];
     Stage stage[QGB_MAX_STAGES];
     Op<real> op[QGB_MAX_OPS];
 };
+
+/* Cut the lanes [row_lanes, n) of tile-lane set S into tensor-map groups (see PassProgram).
+ * Returns the number of groups (may exceed QGB_MAX_GROUPS: the arrays are filled up to that). */
+inline int tile_groups(uint64_t S, int n, int row_lanes, int8_t *start, int8_t *t_bits, int8_t *r_bits) {
+    int count = 0;
+    auto emit = [&](int s, int t, int r) {
+        if (count < QGB_MAX_GROUPS) {
+            start[count] = (int8_t)s;
+            t_bits[count] = (int8_t)t;
+            r_bits[count] = (int8_t)r;
+        }
+        ++count;
+    };
+    int lane = row_lanes;
+    while (lane < n) {
+        int s = lane, t = 0, r = 0;
+        while (lane < n && ((S >> lane) & 1ull)) ++t, ++lane;
+        while (lane < n && !((S >> lane) & 1ull)) ++r, ++lane;
+        while (t > 8) { /* box dimensions are capped at 256 */
+            emit(s, 8, 0);
+            s += 8;
+            t -= 8;
+        }
+        while (t + r > 30) { /* global dimensions must stay below 2^32 */
+            const int take = 30 - t;
+            emit(s, t, take);
+            s += t + take;
+            r -= take;
+            t = 0;
+        }
+        emit(s, t, r);
+    }
+    return count;
+}
 
 /* one queued gate, always kept in double (glue.cpp:382-405 builds the matrix in double and
  * the processor casts to the state precision at apply time, CPUQubitProcessor.cpp:312). */

@@ -113,6 +113,8 @@ class DistContext:
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
     def bind_stream(self):
         if self.on_cuda and self.stream is None:
+            if hasattr(self.local, 'module_init') and not getattr(self.local, 'initialized', True):
+                self.local.module_init()           # the runtime module initialises lazily
             self.stream = torch.cuda.Stream(device=self.device)
             self.api.set_stream(self.stream.cuda_stream)
 
@@ -196,7 +198,8 @@ class DistQubitStates:
         self.g = 0
         self.perm = []                       # logical lane -> physical lane
         self.pending = []
-        self.peers = None                    # p2p: mapped base pointers of all ranks' shards
+        self.peers = None                    # p2p: mapped pointers of all ranks' shards
+        self.peer_bases = []                 # the IPC mappings behind them (closed on delete)
         self.lane_states = []
 
     @property
@@ -224,13 +227,13 @@ class DistQubitStates:
 
     def _close_peers(self):
         if self.peers:
-            for r, p in enumerate(self.peers):
-                if r != self.ctx.rank and p:
-                    try:
-                        self.ctx.api.call('qgb_ipc_close', p)
-                    except Exception:
-                        pass
+            for base in self.peer_bases:
+                try:
+                    self.ctx.api.call('qgb_ipc_close', base)
+                except Exception:
+                    pass
         self.peers = None
+        self.peer_bases = []
 
     def get_n_lanes(self):
         return self.n_lanes
@@ -560,7 +563,7 @@ class DistQubitProcessor:
             dist.all_gather_into_tensor(everyone, mine, group=ctx.group)
         table = everyone.cpu().numpy().reshape(ctx.world, 65)
         own_ptr, _ = qs.data_ptr()
-        peers = []
+        peers, bases = [], []
         for r in range(ctx.world):
             if r == ctx.rank:
                 peers.append(own_ptr)
@@ -568,8 +571,10 @@ class DistQubitProcessor:
             raw = (C.c_ubyte * 64)(*[int(v) for v in table[r, :64]])
             base = C.c_uint64(0)
             self.api.call('qgb_ipc_open', raw, C.byref(base))
+            bases.append(base.value)
             peers.append(base.value + int(table[r, 64]))
         qs.peers = peers
+        qs.peer_bases = bases
 
     # -- observers ----------------------------------------------------------------------------
     def calc_probability(self, qs, lane):

@@ -21,6 +21,7 @@ using namespace qgb;
 typedef std::complex<double> cd;
 
 static int g_failures = 0;
+static bool g_expect_tma = false;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
@@ -56,10 +57,58 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
         for (int b = 0; b < T - L; ++b) off |= (uint64_t)((c >> b) & 1u) << p.tile_lane[L + b];
         choff[c] = off;
     }
+    /* the out-of-tile references the TMA-staged kernel turns into per-tile op masks */
+    {
+        int expect = 0;
+        for (int o = 0; o < p.n_ops; ++o) {
+            const Op<real> &op = p.op[o];
+            int lane = -1;
+            if (op.kind == OP_GEN && (op.arm & ARM_MUX_OUT)) lane = op.mux_out;
+            if (op.kind == OP_DIAG_OUT) lane = op.bit;
+            if (op.kind == OP_DIAG || op.kind == OP_DIAG_OUT)
+                CHECK(op.m1[0] == op.m[2] && op.m1[1] == op.m[3], "diag op %d: d1 not mirrored into m1", o);
+            if (op.ctrl_out == 0 && lane < 0) continue;
+            CHECK(expect < p.n_out && p.out[expect].op == o && p.out[expect].ctrl_mask == op.ctrl_out &&
+                      p.out[expect].sel_lane == lane,
+                  "out-of-tile reference of op %d missing or wrong", o);
+            ++expect;
+        }
+        CHECK(expect == p.n_out, "%d out-of-tile references, expected %d", p.n_out, expect);
+    }
     std::vector<cd> tile(tile_size);
+    if (g_expect_tma) CHECK(p.n_groups >= 1 && p.n_groups <= QGB_MAX_GROUPS, "tile does not fit a tensor map (%d groups)", p.n_groups);
     for (uint64_t bid = 0; bid < (1ull << (n - T)); ++bid) {
         uint64_t base = 0;
         for (int i = 0; i < n - T; ++i) base |= ((bid >> i) & 1ull) << p.rest_lane[i];
+        if (p.n_groups >= 1) {
+            /* the TMA view of the same tile (kernels_tma.cu): box element e of the tensor map whose
+             * dimension 0 is the 128-byte row and dimension d + 1 is lane group d must be the
+             * amplitude the cp.async gather puts at tile element e */
+            int consumed = 0;
+            uint64_t coord[QGB_MAX_GROUPS];
+            uint64_t tbase = 0;
+            int tbits_total = p.row_lanes;
+            for (int d = 0; d < p.n_groups; ++d) {
+                const uint64_t rest = (bid >> consumed) & ((1ull << p.grp_r[d]) - 1ull);
+                coord[d] = rest << p.grp_t[d];
+                tbase |= rest << (p.grp_start[d] + p.grp_t[d]);
+                consumed += p.grp_r[d];
+                tbits_total += p.grp_t[d];
+                CHECK(p.grp_t[d] <= 8 && p.grp_t[d] + p.grp_r[d] <= 32, "group %d exceeds the tensor-map limits", d);
+            }
+            CHECK(consumed == n - T && tbits_total == T, "groups do not cover the lanes (%d rest, %d tile)", consumed, tbits_total);
+            CHECK(tbase == base, "tile origin from groups differs");
+            for (uint32_t e = 0; e < tile_size; e += 37) {
+                uint64_t idx = e & ((1u << p.row_lanes) - 1u);
+                uint32_t rem = e >> p.row_lanes;
+                for (int d = 0; d < p.n_groups; ++d) {
+                    const uint64_t x = rem & ((1u << p.grp_t[d]) - 1u);
+                    rem >>= p.grp_t[d];
+                    idx += (coord[d] + x) << p.grp_start[d];
+                }
+                CHECK(idx == (base | choff[e >> L] | (e & lowmask)), "tensor-map element %u maps to a different amplitude", e);
+            }
+        }
         for (uint32_t e = 0; e < tile_size; ++e) tile[e] = amp[base | choff[e >> L] | (e & lowmask)];
         for (int s = 0; s < p.n_stages; ++s) {
             const Stage &st = p.stage[s];
@@ -72,6 +121,10 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                 for (int j = 0; j < K; ++j)
                     if (r & (1 << j)) o |= rb[j];
                 CHECK(st.sro[r] == tile_swizzle(o, sizeof(real) == 4), "stage %d: bad swizzled offset of register %d", s, r);
+                uint32_t x = 0;
+                for (int j = 0; j < K; ++j)
+                    if (r & (1 << j)) x ^= st.xb[j];
+                CHECK(x == st.sro[r] * 2u * sizeof(real), "stage %d: byte XOR constants disagree with register %d", s, r);
             }
             for (uint32_t tid = 0; tid < (1u << (T - K)); ++tid) {
                 uint32_t ebase = 0;
@@ -99,6 +152,25 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                         else if (op.kind == OP_SWAP) want = ARM_SWAP(op.bit);
                         else want = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
                         CHECK(op.arm == want, "arm selector %u of op kind %d bit %d", op.arm, op.kind, op.bit);
+                        /* Op::code, the body selector of the TMA-staged kernel */
+                        const uint32_t all_regs = (1u << (1 << K)) - 1u;
+                        int code = -1;
+                        if (op.kind == OP_GEN && (op.arm & ARM_MUX_REG)) {
+                            for (int j2 = 0; j2 < K; ++j2) {
+                                uint32_t sel = 0;
+                                for (int r = 0; r < (1 << K); ++r)
+                                    if (r & (1 << j2)) sel |= 1u << r;
+                                if (sel == op.regsel) code = OPC_GEN_REGMUX(op.bit, j2);
+                            }
+                            CHECK(op.regmask == all_regs && op.cmt == 0 && op.ctrl_out == 0, "multiplexed op with controls");
+                        } else if (op.kind == OP_GEN) {
+                            code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
+                        } else if (op.kind == OP_SWAP) {
+                            code = OPC_SWAP(op.bit);
+                        } else {
+                            code = op.regsel ? OPC_DIAG_REG : OPC_DIAG_THR;
+                        }
+                        CHECK(op.code == code, "op code %d, expected %d", op.code, code);
                     }
                     const bool active = (ebase & op.cmt) == op.cmt;
                     const cd m0(op.m[0], op.m[1]), m1(op.m[2], op.m[3]), m2(op.m[4], op.m[5]),
@@ -207,7 +279,7 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
 
 template <typename real>
 static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops, int max_stages,
-                     bool merge, uint64_t seed) {
+                     bool merge, uint64_t seed, bool tma = false) {
     std::mt19937_64 rng(seed);
     std::vector<cd> ref(1ull << n), amp;
     std::normal_distribution<double> nd;
@@ -227,6 +299,12 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     cfg.L = L;
     cfg.max_ops = max_ops;
     cfg.max_stages = max_stages;
+    if (tma) { /* what engine.cu sets for the TMA-staged kernel */
+        cfg.row_lanes = cfg.fp32 ? 4 : 3;
+        cfg.max_groups = QGB_MAX_GROUPS;
+        cfg.L = std::max(cfg.L, cfg.row_lanes);
+    }
+    g_expect_tma = tma && n > cfg.row_lanes && std::min(T, n) >= cfg.row_lanes;
     static PassProgram<real> prog;
     int n_pass = 0, n_exec = 0;
     while (!queue.empty()) {
@@ -249,8 +327,8 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     }
     const double tol = sizeof(real) == 4 ? 2e-4 : 1e-11; /* op matrices are rounded to `real` */
     CHECK(err <= tol * scale, "n=%d T=%d L=%d gates=%d: rel err %.3g", n, T, L, n_gates, err / scale);
-    std::printf("ok %s n=%2d T=%2d L=%d gates=%4d passes=%3d merged=%3d relerr=%.2e\n",
-                sizeof(real) == 4 ? "f32" : "f64", n, T, L, n_gates, n_pass, n_merged, err / scale);
+    std::printf("ok %s n=%2d T=%2d L=%d gates=%4d passes=%3d merged=%3d relerr=%.2e%s\n",
+                sizeof(real) == 4 ? "f32" : "f64", n, T, L, n_gates, n_pass, n_merged, err / scale, tma ? " tma" : "");
 }
 
 int main() {
@@ -264,6 +342,16 @@ int main() {
             }
         }
     }
+    /* tile shapes constrained to what a 5-dimensional tensor map can describe (TMA staging) */
+    for (int n : {8, 10, 13, 14}) {
+        for (int T : {8, 9, 11}) {
+            for (int L : {1, 4, 6}) {
+                run_case<double>(n, T, L, 200, 3, QGB_MAX_OPS, QGB_MAX_STAGES, true, seed++, true);
+                run_case<float>(n, std::max(T, 9), L, 80, 2, QGB_MAX_OPS, QGB_MAX_STAGES, true, seed++, true);
+            }
+        }
+    }
+    g_expect_tma = false;
     /* limits and no-merge paths */
     run_case<double>(10, 7, 2, 300, 3, 5, QGB_MAX_STAGES, false, seed++);
     run_case<double>(10, 7, 2, 300, 3, QGB_MAX_OPS, 2, true, seed++);

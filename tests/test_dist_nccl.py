@@ -65,18 +65,24 @@ def _run_world(world, case, dtype_name, prep, exchange):
              for r in range(world)]
     for p in procs:
         p.start()
+    import queue as queue_mod
     results = {}
     try:
         for _ in range(world):
-            rank, out = queue.get(timeout=300)
+            # a rank that raised leaves its peers waiting in a collective: report what arrived
+            rank, out = queue.get(timeout=120 if not results else 20)
             results[rank] = out
+    except queue_mod.Empty:
+        pass
     finally:
         for p in procs:
-            p.join(timeout=30)
+            p.join(timeout=5)
             if p.is_alive():
                 p.kill()
     for rank, out in results.items():
         assert not isinstance(out, str), 'rank {} failed:\n{}'.format(rank, out)
+    assert len(results) == world, 'ranks {} never answered (hang)'.format(
+        sorted(set(range(world)) - set(results)))
     return results
 
 

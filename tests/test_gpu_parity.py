@@ -27,7 +27,8 @@ PROB_TOL = {np.float64: 1e-12, np.float32: 2e-6}
 def default_options(cuda_runtime):
     api = cuda_runtime.get_api()
     for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 11), ('tile_lanes_fp32', 12),
-                        ('low_lanes_fp64', 5), ('low_lanes_fp32', 6), ('max_gates_per_pass', 112)):
+                        ('low_lanes_fp64', 5), ('low_lanes_fp32', 6), ('max_gates_per_pass', 112),
+                        ('tma', 1), ('tma_buffers', 2), ('tile_buffers', 1)):
         api.set_option(name, value)
     yield
 
@@ -319,13 +320,22 @@ def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
     lanes = 'tile_lanes_fp64' if dtype is np.float64 else 'tile_lanes_fp32'
     low = 'low_lanes_fp64' if dtype is np.float64 else 'low_lanes_fp32'
     k = 3 if dtype is np.float64 else 4
-    for t in (k + 5, k + 6, k + 8, k + 9, k + 10):
-        for l in (1, 3, 6):
-            shapes.append({'fuse': 1, lanes: t, low: l})
-    shapes.append(dict(fuse=1, max_gates_per_pass=3))
+    # both staging engines (TMA tensor-map copies / cp.async) over every tile shape
+    for tma, buffers in ((1, 2), (1, 3), (0, 1), (0, 2)):
+        for t in (k + 5, k + 6, k + 8, k + 9, k + 10):
+            for l in (1, 3, 6):
+                shapes.append({'fuse': 1, 'tma': tma, 'tma_buffers' if tma else 'tile_buffers': buffers,
+                               lanes: t, low: l})
+    shapes.append(dict(fuse=1, tma=1, max_gates_per_pass=3))
     for options in shapes:
+        api.stats_reset()
         got = run(**options)
         assert cases.rel_err(got, base) < tol, options
+        stats = api.stats()
+        if options.get('tma', 1):
+            assert stats['tma_passes'] == stats['tile_passes'] > 0, (options, stats)
+        else:
+            assert stats['tma_passes'] == 0 and stats['tile_passes'] > 0, (options, stats)
 
 
 @pytest.mark.parametrize('dtype,n', ((np.float64, 27), (np.float32, 28)))
