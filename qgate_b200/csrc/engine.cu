@@ -204,6 +204,7 @@ struct Options {
     int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
     int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
     int64_t tma = 1;               /* 1: TMA tensor-map staging (kernels_tma.cu), 0: cp.async */
+    int64_t reg_bits_fp64 = 4;     /* amplitudes per thread = 2^this (TMA kernel: 3 or 4)     */
     int64_t tma_buffers = 2;       /* tile buffers per CTA of the TMA kernel (2 or 3)         */
 };
 
@@ -276,7 +277,7 @@ void flush_tiled(QStates *qs) {
     const bool fp32 = sizeof(real) == 4;
     PlanConfig cfg;
     cfg.fp32 = fp32;
-    cfg.K = fp32 ? 4 : 3;
+    cfg.K = fp32 ? 4 : ((g.opt.tma != 0 && g.opt.reg_bits_fp64 == 4) ? 4 : 3);
     cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
@@ -286,7 +287,7 @@ void flush_tiled(QStates *qs) {
     /* ops per TMA pass: their matrices are staged in shared memory (8 complex per op) */
     const int tma_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
     auto smem_bytes = [&](int T, int L, int stages) {
-        return tma ? tma_pass_smem_bytes(qs->prec, T, stages, n_buf, tma_ops)
+        return tma ? tma_pass_smem_bytes(qs->prec, T, cfg.K, stages, n_buf, tma_ops)
                    : tile_pass_smem_bytes(qs->prec, T, L, stages, n_buf);
     };
     while (cfg.T > cfg.K + 5 && smem_bytes(cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
@@ -329,6 +330,7 @@ void flush_tiled(QStates *qs) {
             CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, want_ctas_tma, g.stream));
             g.stats.tma_passes += 1;
         } else {
+            if (tma && prog.K != (fp32 ? 4 : 3)) fail(QGB_ERR_RUNTIME, "planner produced a tile no tensor map describes.");
             CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, tma ? 1 : n_buf, g.stream));
         }
         g.stats.kernel_launches += 1;
@@ -1277,6 +1279,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "ctas_per_sm") g.opt.ctas_per_sm = value;
     else if (k == "tma") g.opt.tma = value;
     else if (k == "tma_buffers") g.opt.tma_buffers = value;
+    else if (k == "reg_bits_fp64") g.opt.reg_bits_fp64 = value;
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH
 }

@@ -47,7 +47,7 @@ cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
 template <typename real>
 cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf, int min_ctas, cudaStream_t stream);
 /* shared memory of one CTA: n_buf tiles, the matrices of n_ops ops, n_stages thread tables */
-size_t tma_pass_smem_bytes(int prec, int T, int n_stages, int n_buf, int n_ops);
+size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops);
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,

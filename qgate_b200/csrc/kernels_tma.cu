@@ -101,29 +101,111 @@ template <> struct Mat8<double> {
         }
     }
 };
+/* complex64: one amplitude (re, im) is one 64-bit register and the arithmetic is the packed
+ * FFMA2 of sm_100 (fma.rn.f32x2): m * q = (mr, mr) * (x, y) + (-mi, mi) * (y, x) — ptxas folds the
+ * broadcast and the half swap into operand modifiers (R.F32, .F32x2.LO_HI), so a 2x2 on a pair
+ * is 8 instructions instead of 16.  A matrix is stored as 12 floats: the four real parts, then
+ * (-mi, mi) of the four entries. */
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 swap2(u64 v) {
+    float lo, hi;
+    upk2(v, lo, hi);
+    return pk2(hi, lo);
+}
+__device__ __forceinline__ u64 as_u64(const float2 &q) { return pk2(q.x, q.y); }
+__device__ __forceinline__ float2 as_f2(u64 v) {
+    float2 q;
+    upk2(v, q.x, q.y);
+    return q;
+}
+
 template <> struct Mat8<float> {
-    float v[8];
+    float r[4]; /* real parts of m00, m01, m10, m11 */
+    u64 ni[4];  /* (-im, im) of the same              */
     __device__ __forceinline__ void load(const float *p) {
         const float4 *q = reinterpret_cast<const float4 *>(p);
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float4 t = q[i];
-            v[4 * i] = t.x;
-            v[4 * i + 1] = t.y;
-            v[4 * i + 2] = t.z;
-            v[4 * i + 3] = t.w;
-        }
+        const float4 t0 = q[0], t1 = q[1], t2 = q[2];
+        r[0] = t0.x, r[1] = t0.y, r[2] = t0.z, r[3] = t0.w;
+        ni[0] = pk2(t1.x, t1.y), ni[1] = pk2(t1.z, t1.w), ni[2] = pk2(t2.x, t2.y), ni[3] = pk2(t2.z, t2.w);
     }
 };
 
-template <typename real>
-__device__ __forceinline__ void pair_2x2(typename Cplx<real>::type &x0, typename Cplx<real>::type &x1,
-                                         const real (&m)[8]) {
-    const real q0r = x0.x, q0i = x0.y, q1r = x1.x, q1i = x1.y;
+template <typename real> struct MatLayout;
+template <> struct MatLayout<double> {
+    static constexpr int kStride = 8; /* reals per matrix in shared memory */
+    /* value k (0..7: re, im of m00, m01, m10, m11) of a matrix -> what is stored at slot i */
+    __device__ static double slot(const double *m, int i) { return m[i]; }
+    __device__ static void factor(const double *blk, int which, double &re, double &im) {
+        re = blk[2 * which], im = blk[2 * which + 1];
+    }
+};
+template <> struct MatLayout<float> {
+    static constexpr int kStride = 12;
+    __device__ static float slot(const float *m, int i) {
+        if (i < 4) return m[2 * i];
+        const int e = (i - 4) >> 1;
+        return ((i - 4) & 1) ? m[2 * e + 1] : -m[2 * e + 1];
+    }
+    /* diagonal factor `which` (0: d0 = m[0..1], 1: d1 = m[2..3]) */
+    __device__ static void factor(const float *blk, int which, float &re, float &im) {
+        re = blk[which], im = blk[5 + 2 * which];
+    }
+};
+
+__device__ __forceinline__ void pair_2x2(double2 &x0, double2 &x1, const Mat8<double> &mt) {
+    const double(&m)[8] = mt.v;
+    const double q0r = x0.x, q0i = x0.y, q1r = x1.x, q1i = x1.y;
     x0.x = m[0] * q0r - m[1] * q0i + m[2] * q1r - m[3] * q1i;
     x0.y = m[0] * q0i + m[1] * q0r + m[2] * q1i + m[3] * q1r;
     x1.x = m[4] * q0r - m[5] * q0i + m[6] * q1r - m[7] * q1i;
     x1.y = m[4] * q0i + m[5] * q0r + m[6] * q1i + m[7] * q1r;
+}
+
+__device__ __forceinline__ void pair_2x2(float2 &x0, float2 &x1, const Mat8<float> &mt) {
+    const u64 q0 = as_u64(x0), q1 = as_u64(x1), q0s = swap2(q0), q1s = swap2(q1);
+    u64 o0 = mul2(pk2(mt.r[0], mt.r[0]), q0);
+    u64 o1 = mul2(pk2(mt.r[2], mt.r[2]), q0);
+    o0 = fma2(mt.ni[0], q0s, o0);
+    o1 = fma2(mt.ni[2], q0s, o1);
+    o0 = fma2(pk2(mt.r[1], mt.r[1]), q1, o0);
+    o1 = fma2(pk2(mt.r[3], mt.r[3]), q1, o1);
+    o0 = fma2(mt.ni[1], q1s, o0);
+    o1 = fma2(mt.ni[3], q1s, o1);
+    x0 = as_f2(o0);
+    x1 = as_f2(o1);
+}
+
+/* a[r] *= (dr + i di) on the registers of `regmask` */
+template <int K>
+__device__ __forceinline__ void lean_phase(double2 (&a)[1 << K], double dr, double di, uint32_t regmask) {
+    apply_phase<double, K>(a, dr, di, regmask);
+}
+template <int K>
+__device__ __forceinline__ void lean_phase(float2 (&a)[1 << K], float dr, float di, uint32_t regmask) {
+    const u64 rr = pk2(dr, dr), ni = pk2(-di, di);
+#pragma unroll
+    for (int r = 0; r < (1 << K); ++r) {
+        if (regmask & (1u << r)) {
+            const u64 q = as_u64(a[r]);
+            a[r] = as_f2(fma2(ni, swap2(q), mul2(rr, q)));
+        }
+    }
 }
 
 /* MODE 0: every pair; 1: pairs allowed by regmask (uniform); 2 / 3: pairs whose register bit J2 is
@@ -138,7 +220,7 @@ __device__ __forceinline__ void lean_gen(typename Cplx<real>::type (&a)[1 << K],
         if (MODE == 2 && (r0 & (1 << J2))) continue;
         if (MODE == 3 && !(r0 & (1 << J2))) continue;
         if (MODE == 1 && !(regmask & (1u << r0))) continue;
-        pair_2x2<real>(a[r0], a[r0 | (1 << J)], m.v);
+        pair_2x2(a[r0], a[r0 | (1 << J)], m);
     }
 }
 
@@ -146,7 +228,7 @@ template <typename real, int K, int J, int J2>
 __device__ __forceinline__ void lean_regmux(typename Cplx<real>::type (&a)[1 << K], const real *mats) {
     if (J == J2) return; /* never planned */
     lean_gen<real, K, J, 2, (J == J2 ? 0 : J2)>(a, mats, 0u);
-    lean_gen<real, K, J, 3, (J == J2 ? 0 : J2)>(a, mats + 8, 0u);
+    lean_gen<real, K, J, 3, (J == J2 ? 0 : J2)>(a, mats + MatLayout<real>::kStride, 0u);
 }
 
 template <typename real, int K, int J>
@@ -196,11 +278,19 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
     case OPC_SWAP(3): if (K > 3) lean_swap<real, K, QGB_J(3)>(a, op.regmask); break;
     case OPC_DIAG_REG: {
         const uint32_t regmask = op.regmask, regsel = op.regsel;
-        apply_phase<real, K>(a, mo[0], mo[1], regmask & ~regsel);
-        apply_phase<real, K>(a, mo[2], mo[3], regmask & regsel);
+        real d0r, d0i, d1r, d1i;
+        MatLayout<real>::factor(mo, 0, d0r, d0i);
+        MatLayout<real>::factor(mo, 1, d1r, d1i);
+        lean_phase<K>(a, d0r, d0i, regmask & ~regsel);
+        lean_phase<K>(a, d1r, d1i, regmask & regsel);
         break;
     }
-    case OPC_DIAG_THR: apply_phase<real, K>(a, mm[0], mm[1], op.regmask); break;
+    case OPC_DIAG_THR: {
+        real dr, di;
+        MatLayout<real>::factor(mm, 0, dr, di); /* the selected block starts with the selected factor */
+        lean_phase<K>(a, dr, di, op.regmask);
+        break;
+    }
     default: break;
     }
 }
@@ -217,14 +307,16 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
     /* SWIZZLE_128B needs 1024-byte aligned tile buffers */
     unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(tiles + NBUF * tile_bytes);
-    real *mats = reinterpret_cast<real *>(full + NBUF + (NBUF & 1)); /* 16-byte aligned: [op][m, m1][8] */
-    uint32_t *lut = reinterpret_cast<uint32_t *>(mats + 16 * prog.n_ops);
+    constexpr int MS = MatLayout<real>::kStride;
+    real *mats = reinterpret_cast<real *>(full + NBUF + (NBUF & 1)); /* 16-byte aligned: [op][m, m1][MS] */
+    uint32_t *lut = reinterpret_cast<uint32_t *>(mats + 2 * MS * prog.n_ops);
     const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
 
     /* the pass's matrices, once per CTA */
-    for (int i = tid; i < 16 * prog.n_ops; i += nthr) {
-        const Op<real> &op = prog.op[i >> 4];
-        mats[i] = (i & 8) ? op.m1[i & 7] : op.m[i & 7];
+    for (int i = tid; i < 2 * MS * prog.n_ops; i += nthr) {
+        const int o = i / (2 * MS), w = i - o * (2 * MS);
+        const Op<real> &op = prog.op[o];
+        mats[i] = w >= MS ? MatLayout<real>::slot(op.m1, w - MS) : MatLayout<real>::slot(op.m, w);
     }
 
     /* per stage: byte offset (inside a tile buffer) of this thread's base element */
@@ -333,10 +425,10 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
 
             {
                 uint32_t bit = 1u << st.op_begin;
-                const real *mo = mats + 16 * st.op_begin;
-                for (int o = st.op_begin; o < st.op_end; ++o, bit <<= 1, mo += 16) {
+                const real *mo = mats + 2 * MS * st.op_begin;
+                for (int o = st.op_begin; o < st.op_end; ++o, bit <<= 1, mo += 2 * MS) {
                     if (!(eff & bit)) continue;
-                    lean_apply_op<real, K>(a, prog.op[o], mo, mo + ((sel & bit) ? 8 : 0));
+                    lean_apply_op<real, K>(a, prog.op[o], mo, mo + ((sel & bit) ? MS : 0));
                 }
             }
 
@@ -449,7 +541,7 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
     TmaGeometry geo;
     rc = encode_map<real>(prog, amp, &map, &geo);
     if (rc != cudaSuccess) return rc;
-    const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.n_stages, n_buf, prog.n_ops);
+    const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.K, prog.n_stages, n_buf, prog.n_ops);
     const int nthr = 1 << (prog.T - prog.K);
     if (n_buf >= 3) {
         if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 3>(prog, map, geo, smem, stream);
@@ -464,13 +556,12 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
 
 } // namespace
 
-size_t tma_pass_smem_bytes(int prec, int T, int n_stages, int n_buf, int n_ops) {
+size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops) {
     const size_t elem = prec == 1 ? 16 : 8;
-    const int K = prec == 1 ? QGB_K64 : QGB_K32;
     size_t tiles = n_buf * (elem << T);
     tiles = (tiles + 1023) & ~(size_t)1023;
     /* + mbarriers, the matrices of up to QGB_MAX_OPS ops, the per-stage thread table, alignment slack */
-    return tiles + 8 * (n_buf + 1) + 8 * elem * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
+    return tiles + 8 * (n_buf + 1) + (prec == 1 ? 128 : 96) * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
 }
 
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
@@ -482,9 +573,11 @@ cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
 template <>
 cudaError_t launch_tma_pass<double>(const PassProgram<double> &prog, void *amp, int n_buf, int min_ctas,
                                     cudaStream_t stream) {
-    if (prog.K != QGB_K64 || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
+    if ((prog.K != 3 && prog.K != 4) || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
         return cudaErrorInvalidValue;
-    return launch_tma_by_shape<double, QGB_K64>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream);
+    /* 4 register bits: 16 complex128 per thread, CTAs of half as many threads (up to 128 registers) */
+    if (prog.K == 4) return launch_tma_by_shape<double, 4>(prog, amp, 1, n_buf >= 3 ? 3 : 2, 2, stream);
+    return launch_tma_by_shape<double, 3>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream);
 }
 
 template <>

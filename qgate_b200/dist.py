@@ -556,12 +556,14 @@ class DistQubitProcessor:
         handle = (C.c_ubyte * 64)()
         offset = C.c_int64(0)
         self.api.call('qgb_qstates_ipc_export', qs.local.ptr, handle, C.byref(offset))
-        mine = torch.tensor(list(bytes(handle)) + [offset.value], dtype=torch.int64,
-                            device=ctx.device)
-        everyone = torch.empty(ctx.world * 65, dtype=torch.int64, device=ctx.device)
+        # everything on the engine's stream, the host read included: a read issued on another
+        # stream would race with the all-gather and open a garbage handle
         with ctx.stream_ctx():
+            mine = torch.tensor(list(bytes(handle)) + [offset.value], dtype=torch.int64,
+                                device=ctx.device)
+            everyone = torch.empty(ctx.world * 65, dtype=torch.int64, device=ctx.device)
             dist.all_gather_into_tensor(everyone, mine, group=ctx.group)
-        table = everyone.cpu().numpy().reshape(ctx.world, 65)
+            table = everyone.cpu().numpy().reshape(ctx.world, 65)
         own_ptr, _ = qs.data_ptr()
         peers, bases = [], []
         for r in range(ctx.world):

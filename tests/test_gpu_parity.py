@@ -28,7 +28,8 @@ def default_options(cuda_runtime):
     api = cuda_runtime.get_api()
     for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 11), ('tile_lanes_fp32', 12),
                         ('low_lanes_fp64', 5), ('low_lanes_fp32', 6), ('max_gates_per_pass', 112),
-                        ('tma', 1), ('tma_buffers', 2), ('tile_buffers', 1)):
+                        ('tma', 1), ('tma_buffers', 2), ('tile_buffers', 1), ('reg_bits_fp64', 4),
+                        ('ctas_per_sm', 0)):
         api.set_option(name, value)
     yield
 
@@ -327,6 +328,9 @@ def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
                 shapes.append({'fuse': 1, 'tma': tma, 'tma_buffers' if tma else 'tile_buffers': buffers,
                                lanes: t, low: l})
     shapes.append(dict(fuse=1, tma=1, max_gates_per_pass=3))
+    if dtype is np.float64:
+        for t in (8, 9, 11, 12):
+            shapes.append(dict(fuse=1, tma=1, tma_buffers=2, reg_bits_fp64=3, tile_lanes_fp64=t, low_lanes_fp64=5))
     for options in shapes:
         api.stats_reset()
         got = run(**options)
