@@ -375,7 +375,8 @@ def main():
     avg_pass_ms = (device_ms - exch_ms) / max(1, tile_passes)
     peak, peak_src = measured_peak()
     achieved = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'tile_pass_kernel', 'achieved': achieved, 'peak': peak,
+    kernel_name = 'tma_pass_kernel' if stats.get('tma_passes', 0) == tile_passes else 'tile_pass_kernel'
+    roofline = {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                 'peak_source': peak_src, 'bytes_per_launch': pass_bytes,
                 'avg_launch_ms': avg_pass_ms, 'launches_per_step': tile_passes / args.steps,
@@ -400,34 +401,53 @@ def main():
 
     # -- e2e leg: public API on host objects ----------------------------------------------------
     e2e = None
-    if not args.no_e2e and not distributed:
+    if not args.no_e2e:
         q, ops = circuits.random_u3_cx(S, n, args.depth, seed=args.seed)
         e2e_steps = max(1, min(args.steps, 3))
         readback = 4096
 
+        split = {'create_s': 0., 'run_s': 0., 'observe_s': 0., 'terminate_s': 0.}
+
         def e2e_step():
-            sim = qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static)
-            sim.run(ops)
+            t0 = time.perf_counter()
+            prefs = {'sharding': {'exchange': args.exchange}} if distributed else {}
+            sim = qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static,
+                                            **prefs)
+            t1 = time.perf_counter()
+            sim.run(ops)                       # returns after the device has finished (synchronize)
+            t2 = time.perf_counter()
             sim.qubits.set_ordering(q)
             p = sim.qubits.calc_probability(q[n - 1])
             head = sim.qubits.states[:readback]
+            t3 = time.perf_counter()
             sim.terminate()
+            t4 = time.perf_counter()
+            for key, dt in zip(('create_s', 'run_s', 'observe_s', 'terminate_s'),
+                               (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                split[key] += dt
             return p, head
 
         e2e_step()                        # warm-up (allocator, planner caches)
         barrier()
         api.stats_reset()
+        for key in split:
+            split[key] = 0.
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             p, head = e2e_step()
         barrier()
         e2e_s = time.perf_counter() - t0
+        if distributed:                          # slowest rank
+            tt = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_s = float(tt.item())
         st = api.stats()
         assert abs(float(np.sum(np.abs(head) ** 2))) <= 1. and 0. <= p <= 1.
         e2e = {'value': upd * e2e_steps / e2e_s, 'unit': UNIT,
                'h2d_bytes_per_step': st['h2d_bytes'] // e2e_steps,
                'd2h_bytes_per_step': st['d2h_bytes'] // e2e_steps,
                'ms_per_step': 1e3 * e2e_s / e2e_steps, 'steps': e2e_steps,
+               'split_ms': {k: 1e3 * v / e2e_steps for k, v in split.items()},
                'api': 'qgate_b200.simulator.cuda().run(circuit); qubits.calc_probability; '
                       'qubits.states[:4096]'}
 

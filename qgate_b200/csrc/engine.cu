@@ -205,7 +205,8 @@ struct Options {
     int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
     int64_t tma = 1;               /* 1: TMA tensor-map staging (kernels_tma.cu), 0: cp.async */
     int64_t reg_bits_fp64 = 4;     /* amplitudes per thread = 2^this (TMA kernel: 3 or 4)     */
-    int64_t tma_buffers = 2;       /* tile buffers per CTA of the TMA kernel (2 or 3)         */
+    int64_t tma_buffers = 0;       /* tile buffers per CTA of the TMA kernel: 2, 3, 0 = 2 for  */
+                                   /* complex128, 3 for complex64 (measured best, profiles/)  */
 };
 
 struct Engine {
@@ -283,7 +284,8 @@ void flush_tiled(QStates *qs) {
     cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
     const bool tma = g.opt.tma != 0;
-    const int n_buf = tma ? (g.opt.tma_buffers >= 3 ? 3 : 2) : (g.opt.tile_buffers == 2 ? 2 : 1);
+    const int tma_buf = g.opt.tma_buffers == 0 ? (fp32 ? 3 : 2) : (g.opt.tma_buffers >= 3 ? 3 : 2);
+    const int n_buf = tma ? tma_buf : (g.opt.tile_buffers == 2 ? 2 : 1);
     /* ops per TMA pass: their matrices are staged in shared memory (8 complex per op) */
     const int tma_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
     auto smem_bytes = [&](int T, int L, int stages) {
@@ -335,6 +337,7 @@ void flush_tiled(QStates *qs) {
         }
         g.stats.kernel_launches += 1;
         g.stats.tile_passes += 1;
+        g.stats.h2d_bytes += (int64_t)sizeof(prog) + 256; /* the pass program travels as kernel parameters */
         g.stats.gates_executed += st.gates_in_pass;
         g.stats.pass_bytes += (int64_t)(2 * qs->bytes());
     }
