@@ -71,13 +71,20 @@ def _tensor_view(ptr, nbytes, on_cuda, device):
 
 class Gate:
     """One deferred gate in logical-lane coordinates."""
-    __slots__ = ('mat', 'ctrls', 'target', 'diag')
+    __slots__ = ('mat', 'ctrls', 'target', 'diag', 'xmask', 'zmask')
 
     def __init__(self, mat, ctrls, target):
         self.mat = mat                       # ctypes c_double[8]
         self.ctrls = ctrls
         self.target = target
         self.diag = all(mat[i] == 0. for i in _DIAG_ZERO)
+        # lanes the gate acts on non-diagonally / diagonally (a control acts as |1><1|): two gates
+        # commute when, on every lane they share, both act diagonally
+        self.xmask = 0 if self.diag else (1 << target)
+        z = (1 << target) if self.diag else 0
+        for c in ctrls:
+            z |= 1 << c
+        self.zmask = z
 
 
 class DistContext:
@@ -314,9 +321,16 @@ class DistQubitProcessor:
 
     def _scale_all(self, qs, re, im, local_ctrls=()):
         """Multiply every local amplitude (with the local controls set) by re + i im."""
-        lane = next(l for l in range(qs.n_local) if l not in local_ctrls)
-        mat = (C.c_double * 8)(re, im, 0., 0., 0., 0., re, im)
-        self._apply_raw(qs, mat, list(local_ctrls), lane)
+        free = [l for l in range(qs.n_local) if l not in local_ctrls]
+        if free:
+            mat = (C.c_double * 8)(re, im, 0., 0., 0., 0., re, im)
+            self._apply_raw(qs, mat, list(local_ctrls), free[0])
+        else:
+            # every local lane is a control: one of them becomes the target of diag(1, factor)
+            ctrls = list(local_ctrls)
+            lane = ctrls.pop()
+            mat = (C.c_double * 8)(1., 0., 0., 0., 0., 0., re, im)
+            self._apply_raw(qs, mat, ctrls, lane)
 
     def _apply_raw(self, qs, mat, ctrls, target):
         lp = self._lp(qs)
@@ -377,26 +391,36 @@ class DistQubitProcessor:
                 self._apply_raw(qs, gate.mat, [qs.perm[c] for c in gate.ctrls],
                                 qs.perm[gate.target])
             return
-        # next non-diagonal use of every logical lane, for the victim choice
-        uses = [[] for _ in range(qs.n_lanes)]
-        for idx, gate in enumerate(gates):
-            if not gate.diag:
-                uses[gate.target].append(idx)
-        cursor = [0] * qs.n_lanes
+        # Gates run as early as commutation allows: a non-diagonal gate on a global lane (and
+        # everything behind it that does not commute with it) waits, the rest of the queue goes
+        # on.  Only when nothing more can run do lanes trade places, so one exchange serves a
+        # whole light cone of gates instead of one gate.
+        pending = gates
+        while pending:
+            pending = self._apply_unblocked(qs, pending)
+            if pending:
+                self._swap_in(qs, pending)
 
-        def next_use(lane, now):
-            u, c = uses[lane], cursor[lane]
-            while c < len(u) and u[c] < now:
-                c += 1
-            cursor[lane] = c
-            return u[c] if c < len(u) else len(gates)                      # never again
-
+    def _apply_unblocked(self, qs, pending):
+        """Apply, in order, every gate that needs no exchange and commutes with all the gates
+        skipped before it; returns the skipped gates (order kept)."""
         n_local = qs.n_local
-        self._horizon = len(gates)
-        for idx, gate in enumerate(gates):
-            if not gate.diag and qs.perm[gate.target] >= n_local:
-                self._swap_in(qs, idx, next_use)
-            self._apply_local(qs, gate)
+        full = (1 << qs.n_lanes) - 1
+        perm = qs.perm
+        blocked_x = blocked_z = 0
+        rest = []
+        for idx, gate in enumerate(pending):
+            if blocked_x == full:
+                rest.extend(pending[idx:])
+                break
+            x, z = gate.xmask, gate.zmask
+            if (x & (blocked_x | blocked_z)) or (z & blocked_x) or (x and perm[gate.target] >= n_local):
+                rest.append(gate)
+                blocked_x |= x
+                blocked_z |= z
+            else:
+                self._apply_local(qs, gate)
+        return rest
 
     def _apply_local(self, qs, gate):
         n_local = qs.n_local
@@ -420,25 +444,45 @@ class DistQubitProcessor:
         self._scale_all(qs, re, im, local_ctrls)
 
     # -- lane exchange -------------------------------------------------------------------------
-    def _swap_in(self, qs, now, next_use):
-        """Trade global lanes that are needed soon for local lanes that are needed late."""
+    LOOKAHEAD = 2048        # gates of the blocked queue the victim choice looks at
+
+    def _swap_in(self, qs, pending):
+        """Nothing in `pending` can run: trade every global lane a waiting non-diagonal gate
+        targets for a local lane.  The victims are the local lanes whose absence blocks the
+        least of the waiting queue (each candidate is scored by how many of the next LOOKAHEAD
+        gates could still run if that lane alone were global)."""
         n_local = qs.n_local
         phys_to_logical = [0] * qs.n_lanes
         for logical, p in enumerate(qs.perm):
             phys_to_logical[p] = logical
-        min_victim = 1 if np.dtype(qs.dtype) == np.float32 else 0
-        min_victim = max(min_victim, 0)
-        # global lanes with an upcoming non-diagonal gate, soonest first; local lanes, the one
-        # needed latest first (ties: the highest lane, which keeps the moved blocks contiguous)
-        glob = sorted(((next_use(phys_to_logical[p], now), p) for p in range(n_local, qs.n_lanes)))
-        loc = sorted(((next_use(phys_to_logical[p], now), p) for p in range(min_victim, n_local)),
-                     reverse=True)
-        pairs = []
-        for (g_use, g_pos), (l_use, l_pos) in zip(glob, loc):
-            if g_use < l_use and (g_use < self._horizon or not pairs):
-                pairs.append((g_pos, l_pos))
-        if not pairs:
+        window = pending[:self.LOOKAHEAD]
+        wanted = []                                   # global physical lanes, soonest use first
+        for gate in window:
+            p = qs.perm[gate.target]
+            if gate.xmask and p >= n_local and p not in wanted:
+                wanted.append(p)
+        if not wanted:
+            raise RuntimeError('blocked gate queue without a global target.')
+        min_victim = 1 if np.dtype(qs.dtype) == np.float32 else 0   # 16-byte exchange units
+        if n_local >= 12:
+            min_victim = 5       # victims at lane >= 5 move runs of >= 512 bytes over the link
+        cand_phys = list(range(min_victim, n_local))
+        if not cand_phys:
             raise RuntimeError('no local lane available for an exchange.')
+        cand = np.array([1 << phys_to_logical[p] for p in cand_phys], dtype=np.uint64)
+        bx = np.zeros(len(cand), np.uint64)
+        bz = np.zeros(len(cand), np.uint64)
+        score = np.zeros(len(cand), np.int64)
+        zero = np.uint64(0)
+        for gate in window:
+            x, z = np.uint64(gate.xmask), np.uint64(gate.zmask)
+            blocked = ((x & (bx | bz)) != zero) | ((z & bx) != zero) | ((x & cand) != zero)
+            score += ~blocked
+            bx |= np.where(blocked, x, zero)
+            bz |= np.where(blocked, z, zero)
+        # best score first; ties: the highest lane (keeps the moved blocks contiguous)
+        order = sorted(range(len(cand_phys)), key=lambda i: (-int(score[i]), -cand_phys[i]))
+        pairs = [(g_pos, cand_phys[i]) for g_pos, i in zip(wanted, order)]
         self.exchange(qs, pairs)
 
     def make_local(self, qs, lane):

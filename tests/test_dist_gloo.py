@@ -32,6 +32,14 @@ def _build(case):
         q, ops = circuits.qft(S, 9)
     elif case == 'grover':
         q, ops = circuits.grover(S, 8, 2, 0x5A)
+    elif case == 'mcz':
+        # diagonal gate on a global lane whose controls cover EVERY local lane, and the same with
+        # a non-diagonal target; then enough dense gates to force exchanges both ways
+        q = S.new_qregs(7)
+        ops = [S.H(qr) for qr in q] + [S.ctrl(q[:-1]).Z(q[-1]), S.ctrl(q[:-1]).U1(0.3)(q[-1]),
+                                       S.ctrl(q[1:]).Rz(0.7)(q[0]), S.ctrl(q[:-1]).X(q[-1])]
+        ops += [S.Ry(0.2 * (i + 1))(qr) for i, qr in enumerate(q)] + [S.ctrl(q[1:]).Z(q[0])]
+        ops += circuits.random_u3_cx(S, 7, 3, seed=5, qregs=q)[1]
     elif case == 'measure':
         q, ops = circuits.random_u3_cx(S, 8, 3, seed=8)
         refs = S.new_references(4)
@@ -127,7 +135,7 @@ def _expected(case, dtype_name, prep, seed_rank0):
 
 
 @pytest.mark.parametrize('world', (2, 4))
-@pytest.mark.parametrize('case', ('random', 'zoo', 'qft', 'grover', 'measure'))
+@pytest.mark.parametrize('case', ('random', 'zoo', 'qft', 'grover', 'measure', 'mcz'))
 def test_sharded_matches_single(world, case, ref_runtime):
     prep = 'one_static'
     results = _run_world(world, case, 'float64', prep)
@@ -145,7 +153,7 @@ def test_sharded_matches_single(world, case, ref_runtime):
     # every rank saw the same thing
     for key in ('states', 'samples'):
         assert np.array_equal(results[0][key], results[world - 1][key])
-    if case in ('random', 'zoo', 'grover'):
+    if case in ('random', 'zoo', 'grover', 'mcz'):
         assert results[0]['stats']['exchanges'] > 0, 'no lane exchange was exercised'
 
 

@@ -87,7 +87,7 @@ def _run_world(world, case, dtype_name, prep, exchange):
 
 
 @pytest.mark.parametrize('exchange', ('p2p', 'collective'))
-@pytest.mark.parametrize('case', ('random', 'zoo', 'qft', 'grover', 'measure'))
+@pytest.mark.parametrize('case', ('random', 'zoo', 'qft', 'grover', 'measure', 'mcz'))
 def test_sharded_cuda_matches_reference(case, exchange, ref_runtime):
     if _n_gpus() < 2:
         pytest.skip('needs >= 2 GPUs')
@@ -105,7 +105,7 @@ def test_sharded_cuda_matches_reference(case, exchange, ref_runtime):
             assert np.array_equal(got[key], want[key]), (rank, key)
         if 'bits' in want:
             assert np.array_equal(got['bits'], want['bits']), rank
-    if case in ('random', 'zoo', 'grover'):
+    if case in ('random', 'zoo', 'grover', 'mcz'):
         assert results[0]['stats']['exchanges'] > 0, 'no lane exchange was exercised'
 
 
