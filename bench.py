@@ -150,6 +150,19 @@ def measured_peak():
         return 6650., 'fallback (B200_PROFILING.md)'
 
 
+def measured_traffic(dtype, qubits, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json); None when no
+    capture matches the dtype / shard size / kernel."""
+    try:
+        with open(os.path.join(REPO, 'profiles', 'traffic.json')) as f:
+            table = json.load(f)
+        entry = table['{}_{}q'.format(dtype, qubits)]
+        return entry['dram_bytes_per_launch'] if entry['kernel'] == kernel else None
+    except Exception:
+        return None
+
+
 # ---- reference CPU runtime (oracle/_ref): cpu_baseline leg and --impl reference ---------------
 
 class ReferenceCpu:
@@ -377,7 +390,8 @@ def main():
     achieved = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
     kernel_name = 'tma_pass_kernel' if stats.get('tma_passes', 0) == tile_passes else 'tile_pass_kernel'
     roofline = {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': measured_traffic(args.dtype, args.qubits, kernel_name),
                 'peak_source': peak_src, 'bytes_per_launch': pass_bytes,
                 'avg_launch_ms': avg_pass_ms, 'launches_per_step': tile_passes / args.steps,
                 'gates_per_launch': len(gates) * args.steps / max(1, tile_passes)}

@@ -146,13 +146,17 @@ struct MemPool {
         const size_t c = it->second;
         live.erase(it);
         live_bytes -= c;
-        /* keep small and medium blocks; give the big ones back so another shape can use them */
-        if (c <= (size_t(1) << 28)) {
-            cached[c].push_back(p);
-            cached_bytes += c;
-        } else {
+        /* Keep the block for the next qstates of this size class: cudaMalloc + cudaFree of a 16 GiB
+         * state vector cost ~0.3 s each (bench.py e2e split), re-use is free and stream-ordered.
+         * Big blocks are capped: at most one per size class and 72 GiB in total; an allocation
+         * that fails trims the whole cache and retries (alloc). */
+        const bool big = c > (size_t(1) << 28);
+        if (big && (!cached[c].empty() || cached_bytes + c > (size_t(72) << 30))) {
             cudaFree(p);
+            return;
         }
+        cached[c].push_back(p);
+        cached_bytes += c;
     }
 
     void clear() {
@@ -196,9 +200,14 @@ struct Options {
     int64_t fuse = 1;
     int64_t merge = 1;
     int64_t tile_lanes_fp64 = 11, tile_lanes_fp32 = 12;
-    int64_t low_lanes_fp64 = 5, low_lanes_fp32 = 6;
+    /* low contiguous lanes forced into every tile; 0 = by staging engine: the 128-byte row of the
+     * TMA tensor map (3 complex128 / 4 complex64), 5 / 6 for the cp.async kernel's coalescing */
+    int64_t low_lanes_fp64 = 0, low_lanes_fp32 = 0;
     int64_t max_gates_per_pass = QGB_MAX_OPS;
-    int64_t max_cost = 1 << 30;
+    /* cap on the summed op cost of a pass (dense 2x2 = 4, diagonal / swap = 1); 0 = 32 for
+     * complex128 on the TMA kernel — 8 dense ops keep a pass near the point where the FP64 pipe
+     * and HBM take the same time (profiles/r1s sweep) — unlimited otherwise */
+    int64_t max_cost = 0;
     int64_t lookahead = 4096;
     int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
     int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
@@ -281,7 +290,9 @@ void flush_tiled(QStates *qs) {
     cfg.K = fp32 ? 4 : ((g.opt.tma != 0 && g.opt.reg_bits_fp64 == 4) ? 4 : 3);
     cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
-    cfg.L = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
+    const int low_opt = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
+    const int low_auto = g.opt.tma != 0 ? (fp32 ? 4 : 3) : (fp32 ? 6 : 5);
+    cfg.L = low_opt > 0 ? low_opt : low_auto;
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
     const bool tma = g.opt.tma != 0;
     const int tma_buf = g.opt.tma_buffers == 0 ? (fp32 ? 3 : 2) : (g.opt.tma_buffers >= 3 ? 3 : 2);
@@ -295,7 +306,7 @@ void flush_tiled(QStates *qs) {
     while (cfg.T > cfg.K + 5 && smem_bytes(cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
-    if (cfg.T >= qs->n_lanes) cfg.L = std::min((int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64), cfg.T);
+    if (cfg.T >= qs->n_lanes) cfg.L = std::min(low_opt > 0 ? low_opt : low_auto, cfg.T);
     if (tma) {
         /* the 128-byte row of the tensor map lies inside every tile */
         cfg.row_lanes = fp32 ? 4 : 3;
@@ -321,7 +332,7 @@ void flush_tiled(QStates *qs) {
         while (ms > 2 && smem_bytes(cfg.T, cfg.L, ms) > budget) --ms;
         cfg.max_stages = ms;
     }
-    cfg.max_cost = (int)g.opt.max_cost;
+    cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : ((tma && !fp32) ? 32 : (1 << 30));
     cfg.lookahead = (int)g.opt.lookahead;
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
     PlanStats st;

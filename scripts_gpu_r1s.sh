@@ -1,0 +1,21 @@
+#!/bin/bash
+# round-1 GPU session S: low-lane sweep, K=4 complex128 profile, full bench lines
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -m gpu -q -x ) 2>&1 | tail -25 > gpurun_out/r1s_pytest_gpu.log
+tail -5 gpurun_out/r1s_pytest_gpu.log
+Q="--steps 2 --warmup 1 --no-e2e --no-cpu-baseline --depth 60"
+show() { python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:300]); continue
+    r=d['roofline']; print('value %.3e ms/step %.0f passes %d gates/pass %.1f avg_ms %.2f GB/s %.0f frac %.3f p0 %.9f'%(d['value'],d['ms_per_step'],r['launches_per_step'],r['gates_per_launch'],r['avg_launch_ms'],r['achieved'],r['frac'],d['p0_check']))
+"; }
+for opt in "" "--option low_lanes_fp64=3" "--option low_lanes_fp64=4" "--option low_lanes_fp64=3 --option max_gates_per_pass=12" "--option low_lanes_fp64=3 --option max_gates_per_pass=8" "--option low_lanes_fp64=3 --option max_gates_per_pass=6"; do
+  echo "== f64 $opt"; timeout 300 python bench.py $Q $opt 2>&1 | show
+done
+for opt in "" "--option low_lanes_fp32=4" "--option low_lanes_fp32=4 --option max_gates_per_pass=12" "--option low_lanes_fp32=4 --option max_gates_per_pass=8"; do
+  echo "== f32 $opt"; timeout 300 python bench.py $Q --dtype f32 $opt 2>&1 | show
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tma_pass -s 6 -c 2 -o gpurun_out/r1s_tma_f64_k4 -f python bench.py --qubits 28 --steps 1 --warmup 1 --depth 10 --no-e2e --no-cpu-baseline > gpurun_out/r1s_ncu_full.log 2>&1
+tail -2 gpurun_out/r1s_ncu_full.log
