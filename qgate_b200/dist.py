@@ -480,8 +480,12 @@ class DistQubitProcessor:
             score += ~blocked
             bx |= np.where(blocked, x, zero)
             bz |= np.where(blocked, z, zero)
-        # best score first; ties: the highest lane (keeps the moved blocks contiguous)
-        order = sorted(range(len(cand_phys)), key=lambda i: (-int(score[i]), -cand_phys[i]))
+        # best score first; among lanes within 10% of the best, the highest (the exchange moves
+        # runs of 2^lane amplitudes: longer runs use the links better)
+        best = int(score.max())
+        order = sorted(range(len(cand_phys)),
+                       key=lambda i: (-(best if int(score[i]) * 10 >= best * 9 else int(score[i])),
+                                      -cand_phys[i]))
         pairs = [(g_pos, cand_phys[i]) for g_pos, i in zip(wanted, order)]
         self.exchange(qs, pairs)
 
