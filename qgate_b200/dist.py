@@ -112,7 +112,7 @@ class DistContext:
         self.shard_min_lanes = max(int(shard_min_lanes), 2 * self.g + 2)
         self.stream = None
         self.stats = {'exchanges': 0, 'exchange_bytes': 0, 'exchange_lanes': 0,
-                      'local_swaps': 0}
+                      'local_swaps': 0, 'sharded_joins': 0, 'gathered_operands': 0}
         self.timing = False          # bench.py: CUDA events around every exchange
         self._exchange_events = []
         self._barrier_buf = None
@@ -691,30 +691,75 @@ class DistQubitProcessor:
         qs1.perm = [0]
         qs1.pending = []
 
+    def _gather_replica(self, src):
+        """A sharded qstates as a local, unsharded copy on every rank (all-gather of the shards:
+        rank-major = the global lanes on top, so the physical lane order is unchanged)."""
+        ctx = self.ctx
+        tmp = ctx.local.create_qubit_states(src.dtype)
+        tmp.processor.initialize_qubit_states(tmp, src.n_lanes)
+        ptr, nbytes = C.c_uint64(0), C.c_int64(0)
+        self.api.call('qgb_qstates_data_ptr', tmp.ptr, C.byref(ptr), C.byref(nbytes))
+        whole = _tensor_view(ptr.value, nbytes.value, ctx.on_cuda, ctx.device)
+        with ctx.stream_ctx():
+            dist.all_gather_into_tensor(whole, src.tensor(), group=ctx.group)
+            if ctx.on_cuda:
+                ctx.stream.synchronize()
+        return tmp
+
     def join(self, qs, qs_list, n_new):
+        """Kronecker product of the groups (qubits_handler.py:60-89; the LAST list element holds
+        the lowest lanes).  Replicated operands multiply locally.  One sharded operand keeps its
+        global lanes: every rank multiplies ITS shard with the replicated operands, no traffic.
+        Further sharded operands are first gathered into replicas (they must fit one GPU)."""
         for src in qs_list:
             self._run_pending(src)
-            if src.g:
-                raise NotImplementedError('join of a sharded qstates is not supported yet: '
-                                          'use circuit_prep=static / one_static for sharded sizes.')
         lp = self._lp(qs)
-        srcs = [src.local for src in qs_list]
-        if qs.g == 0:
-            lp.join(qs.local, srcs, n_new)
+        sharded = [src for src in qs_list if src.g]
+        temps = []
+        if not sharded:
+            srcs = [src.local for src in qs_list]
+            if qs.g == 0:
+                lp.join(qs.local, srcs, n_new)
+            else:
+                ptrs = self.api.handle_array([s.ptr for s in srcs])
+                self.api.call('qgb_qproc_join_shard', lp.ptr, qs.local.ptr, ptrs, len(srcs), n_new,
+                              qs.n_lanes, self.ctx.rank << qs.n_local)
+            keep = None
         else:
-            ptrs = self.api.handle_array([s.ptr for s in srcs])
-            self.api.call('qgb_qproc_join_shard', lp.ptr, qs.local.ptr, ptrs, len(srcs), n_new,
-                          qs.n_lanes, self.ctx.rank << qs.n_local)
-        # the LAST list element holds the lowest lanes (qubits_handler.py:73-89)
-        perm, offset = [0] * qs.n_lanes, 0
+            if qs.g == 0:
+                raise RuntimeError('join: a sharded operand needs a sharded destination.')
+            keep = max(sharded, key=lambda src: src.n_lanes)
+            srcs = []
+            for src in qs_list:
+                if src is keep or not src.g:
+                    srcs.append(src.local)
+                else:
+                    rep = self._gather_replica(src)
+                    temps.append(rep)
+                    srcs.append(rep)
+            lp.join(qs.local, srcs, n_new)
+            self.ctx.stats['sharded_joins'] += 1
+            self.ctx.stats['gathered_operands'] += len(temps)
+        # logical lane -> physical lane of the product
+        perm = [0] * qs.n_lanes
+        off_log = off_phys = 0
         for src in reversed(qs_list):
-            for logical, p in enumerate(src.perm):
-                perm[offset + logical] = offset + p
-            offset += src.n_lanes
-        for i in range(offset, qs.n_lanes):
-            perm[i] = i
+            if src is keep:
+                for logical, p in enumerate(src.perm):
+                    perm[off_log + logical] = off_phys + p if p < src.n_local \
+                        else qs.n_local + (p - src.n_local)
+                off_phys += src.n_local
+            else:
+                for logical, p in enumerate(src.perm):
+                    perm[off_log + logical] = off_phys + p
+                off_phys += src.n_lanes
+            off_log += src.n_lanes
+        for i in range(qs.n_lanes - off_log):          # new |0> qubits: the top LOCAL lanes
+            perm[off_log + i] = off_phys + i
         qs.perm = perm
         qs.pending = []
+        for rep in temps:
+            rep.delete()
 
 
 class DistSamplingPool:

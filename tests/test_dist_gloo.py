@@ -40,6 +40,20 @@ def _build(case):
                                        S.ctrl(q[1:]).Rz(0.7)(q[0]), S.ctrl(q[:-1]).X(q[-1])]
         ops += [S.Ry(0.2 * (i + 1))(qr) for i, qr in enumerate(q)] + [S.ctrl(q[1:]).Z(q[0])]
         ops += circuits.random_u3_cx(S, 7, 3, seed=5, qregs=q)[1]
+    elif case == 'joins':
+        # two registers grow independently past the sharding threshold (6 lanes), keep taking in
+        # fresh qubits, then get entangled with each other
+        a, b = S.new_qregs(7), S.new_qregs(7)
+        refs = S.new_references(2)
+        ops = []
+        for reg, seed in ((a, 1), (b, 2)):
+            ops += [S.H(reg[0])] + [S.ctrl(reg[i]).X(reg[i + 1]) for i in range(5)]
+            ops += circuits.random_u3_cx(S, 6, 2, seed=seed, qregs=reg[:6])[1]
+            ops += [S.Ry(0.4)(reg[6]), S.ctrl(reg[6]).Rx(0.9)(reg[2])]          # sharded + 1 qubit
+        ops += [S.ctrl(a[1]).X(b[3]), S.ctrl(b[6]).Ry(1.1)(a[0])]                # sharded + sharded
+        ops += circuits.random_u3_cx(S, 14, 2, seed=3, qregs=a + b)[1]
+        ops += [S.measure(refs[0], a[3]), S.H(a[3]), S.ctrl(a[3]).X(b[0]), S.measure(refs[1], b[5])]
+        q = a + b
     elif case == 'measure':
         q, ops = circuits.random_u3_cx(S, 8, 3, seed=8)
         refs = S.new_references(4)
@@ -170,3 +184,21 @@ def test_sharded_float32_and_dynamic_prep(ref_runtime):
     want = _expected('qft', 'float64', 'static', 1234)
     for rank, got in results.items():
         assert np.abs(got['states'] - want['states']).max() < 1e-12
+
+
+@pytest.mark.parametrize('world', (2, 4))
+def test_joins_of_sharded_groups(world, ref_runtime):
+    """Dynamic qubit grouping at sharded sizes: a sharded group absorbs single qubits (one sharded
+    operand, no traffic), two sharded groups join (the smaller is gathered into a replica), and a
+    measurement then separates a lane again."""
+    results = _run_world(world, 'joins', 'float64', 'dynamic')
+    want = _expected('joins', 'float64', 'dynamic', 1234)
+    for rank, got in results.items():
+        assert got['sharded'] == int(np.log2(world))
+        for key in ('states', 'slice', 'states_rev'):
+            assert np.abs(got[key] - want[key]).max() < 1e-12, (rank, key)
+        assert np.abs(got['p0'] - want['p0']).max() < 1e-12
+        assert np.array_equal(got['samples'], want['samples'])
+        assert np.array_equal(got['bits'], want['bits'])
+        assert got['stats']['sharded_joins'] >= 3 and got['stats']['gathered_operands'] >= 1, got['stats']
+        assert got['stats']['sharded_joins'] >= 3 and got['stats']['gathered_operands'] >= 1, got['stats']

@@ -119,3 +119,20 @@ def test_sharded_cuda_float32(exchange, ref_runtime):
         assert got['states'].dtype == np.complex64
         assert np.abs(got['states'] - want['states']).max() < 1e-5
         assert np.mean(got['samples'] == want['samples']) > 0.99
+
+
+@pytest.mark.parametrize('exchange', ('p2p', 'collective'))
+def test_joins_of_sharded_groups_cuda(exchange, ref_runtime):
+    """Dynamic qubit grouping at sharded sizes on GPUs (see tests/test_dist_gloo.py)."""
+    if _n_gpus() < 2:
+        pytest.skip('needs >= 2 GPUs')
+    results = _run_world(2, 'joins', 'float64', 'dynamic', exchange)
+    want = _expected('joins', 'float64', 'dynamic', 1234)
+    for rank, got in results.items():
+        assert got['sharded'] == 1
+        for key in ('states', 'slice', 'states_rev'):
+            assert np.abs(got[key] - want[key]).max() < 1e-12, (rank, key)
+        assert np.abs(got['p0'] - want['p0']).max() < 1e-12
+        assert np.array_equal(got['samples'], want['samples'])
+        assert np.array_equal(got['bits'], want['bits'])
+        assert got['stats']['sharded_joins'] >= 3 and got['stats']['gathered_operands'] >= 1
