@@ -59,13 +59,15 @@ exchange_p2p_kernel(uint4 *__restrict__ local, const __grid_constant__ ExchangeP
             ++n;
         }
     }
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_items; t += stride) {
+    /* item t -> (unit index in this shard, unit index in the peer's shard, peer) */
+    auto locate = [&](uint64_t t, uint64_t &mine, uint64_t &theirs, int &j) {
         const uint64_t rest = t & (n_rest - 1ull);
-        int j = (int)(t >> rest_bits);
+        j = (int)(t >> rest_bits);
         if (j >= s) ++j; /* skip my own block */
         /* the lower-numbered rank of a pair moves the units whose split bit is 0 */
         const uint64_t split_bit = (s < j) ? 0ull : 1ull;
-        uint64_t mine = rest, theirs = rest;
+        mine = rest;
+        theirs = rest;
 #pragma unroll
         for (int n = 0; n < QGB_MAX_EXCHANGE_LANES + 1; ++n) {
             if (n < k + 1) {
@@ -76,6 +78,35 @@ exchange_p2p_kernel(uint4 *__restrict__ local, const __grid_constant__ ExchangeP
                 theirs = insert_bit(theirs, pos[n], bt);
             }
         }
+    };
+    /* four swaps per thread in flight: the remote loads cross NVLink (microseconds), the more of
+     * them are outstanding the better the links are used */
+    constexpr int UNROLL = 4;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + (UNROLL - 1) * stride < n_items; t += UNROLL * stride) {
+        uint64_t mine[UNROLL], theirs[UNROLL];
+        uint4 *remote[UNROLL];
+        uint4 a[UNROLL], b[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            int j;
+            locate(t + u * stride, mine[u], theirs[u], j);
+            remote[u] = reinterpret_cast<uint4 *>(ep.peer[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) b[u] = remote[u][theirs[u]];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) a[u] = local[mine[u]];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            local[mine[u]] = b[u];
+            remote[u][theirs[u]] = a[u];
+        }
+    }
+    for (; t < n_items; t += stride) {
+        uint64_t mine, theirs;
+        int j;
+        locate(t, mine, theirs, j);
         uint4 *remote = reinterpret_cast<uint4 *>(ep.peer[j]);
         const uint4 a = local[mine];
         const uint4 b = remote[theirs];
