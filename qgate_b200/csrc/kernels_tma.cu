@@ -91,6 +91,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <typename real> struct Mat8;
 template <> struct Mat8<double> {
     double v[8];
+    /* diagonal factor `which` (0: d0 = m[0..1], 1: d1 = m[2..3]) */
+    __device__ __forceinline__ void factor(int which, double &re, double &im) const {
+        re = v[2 * which], im = v[2 * which + 1];
+    }
     __device__ __forceinline__ void load(const double *p) {
         const double2 *q = reinterpret_cast<const double2 *>(p);
 #pragma unroll
@@ -138,6 +142,12 @@ __device__ __forceinline__ float2 as_f2(u64 v) {
 template <> struct Mat8<float> {
     float r[4]; /* real parts of m00, m01, m10, m11 */
     u64 ni[4];  /* (-im, im) of the same              */
+    /* diagonal factor `which`: d0 = (m[0], m[1]) -> r[0], ni[0]; d1 = (m[2], m[3]) -> r[1], ni[1] */
+    __device__ __forceinline__ void factor(int which, float &re, float &im) const {
+        float neg;
+        re = r[which];
+        upk2(ni[which], neg, im);
+    }
     __device__ __forceinline__ void load(const float *p) {
         const float4 *q = reinterpret_cast<const float4 *>(p);
         const float4 t0 = q[0], t1 = q[1], t2 = q[2];
@@ -211,9 +221,7 @@ __device__ __forceinline__ void lean_phase(float2 (&a)[1 << K], float dr, float 
 /* MODE 0: every pair; 1: pairs allowed by regmask (uniform); 2 / 3: pairs whose register bit J2 is
  * 0 / 1 (compile time) */
 template <typename real, int K, int J, int MODE, int J2>
-__device__ __forceinline__ void lean_gen(typename Cplx<real>::type (&a)[1 << K], const real *mats, uint32_t regmask) {
-    Mat8<real> m;
-    m.load(mats);
+__device__ __forceinline__ void lean_gen(typename Cplx<real>::type (&a)[1 << K], const Mat8<real> &m, uint32_t regmask) {
 #pragma unroll
     for (int r0 = 0; r0 < (1 << K); ++r0) {
         if (r0 & (1 << J)) continue;
@@ -225,10 +233,14 @@ __device__ __forceinline__ void lean_gen(typename Cplx<real>::type (&a)[1 << K],
 }
 
 template <typename real, int K, int J, int J2>
-__device__ __forceinline__ void lean_regmux(typename Cplx<real>::type (&a)[1 << K], const real *mats) {
+__device__ __forceinline__ void lean_regmux(typename Cplx<real>::type (&a)[1 << K], const Mat8<real> &m0,
+                                            const real *mats) {
     if (J == J2) return; /* never planned */
-    lean_gen<real, K, J, 2, (J == J2 ? 0 : J2)>(a, mats, 0u);
-    lean_gen<real, K, J, 3, (J == J2 ? 0 : J2)>(a, mats + MatLayout<real>::kStride, 0u);
+    Mat8<real> m1;
+    if (sizeof(real) == 4) m1.load(mats + MatLayout<real>::kStride); /* in flight under the first half */
+    lean_gen<real, K, J, 2, (J == J2 ? 0 : J2)>(a, m0, 0u);
+    if (sizeof(real) == 8) m1.load(mats + MatLayout<real>::kStride); /* complex128: no registers to spare */
+    lean_gen<real, K, J, 3, (J == J2 ? 0 : J2)>(a, m1, 0u);
 }
 
 template <typename real, int K, int J>
@@ -247,31 +259,34 @@ __device__ __forceinline__ void lean_swap(typename Cplx<real>::type (&a)[1 << K]
 #define QGB_J(j) ((j) < K ? (j) : 0)
 
 /* One op on the registers of a thread that takes part in it (`mm` = the op's matrix or factor
- * already selected for this thread and tile, `mo` = the op's [m | m1] block). */
+ * already selected for this thread and tile, `mo` = the op's [m | m1] block).  The matrix is
+ * fetched BEFORE the dispatch so the shared-memory latency hides under the switch. */
 template <typename real, int K>
 __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
                                               const real *mo, const real *mm) {
+    Mat8<real> m;
+    m.load(mm);
     switch (op.code) {
-    case OPC_GEN(0): lean_gen<real, K, 0, 0, 0>(a, mm, 0u); break;
-    case OPC_GEN(1): lean_gen<real, K, QGB_J(1), 0, 0>(a, mm, 0u); break;
-    case OPC_GEN(2): lean_gen<real, K, QGB_J(2), 0, 0>(a, mm, 0u); break;
-    case OPC_GEN(3): if (K > 3) lean_gen<real, K, QGB_J(3), 0, 0>(a, mm, 0u); break;
-    case OPC_GEN_MASKED(0): lean_gen<real, K, 0, 1, 0>(a, mm, op.regmask); break;
-    case OPC_GEN_MASKED(1): lean_gen<real, K, QGB_J(1), 1, 0>(a, mm, op.regmask); break;
-    case OPC_GEN_MASKED(2): lean_gen<real, K, QGB_J(2), 1, 0>(a, mm, op.regmask); break;
-    case OPC_GEN_MASKED(3): if (K > 3) lean_gen<real, K, QGB_J(3), 1, 0>(a, mm, op.regmask); break;
-    case OPC_GEN_REGMUX(0, 1): lean_regmux<real, K, 0, QGB_J(1)>(a, mo); break;
-    case OPC_GEN_REGMUX(0, 2): lean_regmux<real, K, 0, QGB_J(2)>(a, mo); break;
-    case OPC_GEN_REGMUX(0, 3): if (K > 3) lean_regmux<real, K, 0, QGB_J(3)>(a, mo); break;
-    case OPC_GEN_REGMUX(1, 0): lean_regmux<real, K, QGB_J(1), 0>(a, mo); break;
-    case OPC_GEN_REGMUX(1, 2): lean_regmux<real, K, QGB_J(1), QGB_J(2)>(a, mo); break;
-    case OPC_GEN_REGMUX(1, 3): if (K > 3) lean_regmux<real, K, QGB_J(1), QGB_J(3)>(a, mo); break;
-    case OPC_GEN_REGMUX(2, 0): lean_regmux<real, K, QGB_J(2), 0>(a, mo); break;
-    case OPC_GEN_REGMUX(2, 1): lean_regmux<real, K, QGB_J(2), QGB_J(1)>(a, mo); break;
-    case OPC_GEN_REGMUX(2, 3): if (K > 3) lean_regmux<real, K, QGB_J(2), QGB_J(3)>(a, mo); break;
-    case OPC_GEN_REGMUX(3, 0): if (K > 3) lean_regmux<real, K, QGB_J(3), 0>(a, mo); break;
-    case OPC_GEN_REGMUX(3, 1): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(1)>(a, mo); break;
-    case OPC_GEN_REGMUX(3, 2): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(2)>(a, mo); break;
+    case OPC_GEN(0): lean_gen<real, K, 0, 0, 0>(a, m, 0u); break;
+    case OPC_GEN(1): lean_gen<real, K, QGB_J(1), 0, 0>(a, m, 0u); break;
+    case OPC_GEN(2): lean_gen<real, K, QGB_J(2), 0, 0>(a, m, 0u); break;
+    case OPC_GEN(3): if (K > 3) lean_gen<real, K, QGB_J(3), 0, 0>(a, m, 0u); break;
+    case OPC_GEN_MASKED(0): lean_gen<real, K, 0, 1, 0>(a, m, op.regmask); break;
+    case OPC_GEN_MASKED(1): lean_gen<real, K, QGB_J(1), 1, 0>(a, m, op.regmask); break;
+    case OPC_GEN_MASKED(2): lean_gen<real, K, QGB_J(2), 1, 0>(a, m, op.regmask); break;
+    case OPC_GEN_MASKED(3): if (K > 3) lean_gen<real, K, QGB_J(3), 1, 0>(a, m, op.regmask); break;
+    case OPC_GEN_REGMUX(0, 1): lean_regmux<real, K, 0, QGB_J(1)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(0, 2): lean_regmux<real, K, 0, QGB_J(2)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(0, 3): if (K > 3) lean_regmux<real, K, 0, QGB_J(3)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(1, 0): lean_regmux<real, K, QGB_J(1), 0>(a, m, mo); break;
+    case OPC_GEN_REGMUX(1, 2): lean_regmux<real, K, QGB_J(1), QGB_J(2)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(1, 3): if (K > 3) lean_regmux<real, K, QGB_J(1), QGB_J(3)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(2, 0): lean_regmux<real, K, QGB_J(2), 0>(a, m, mo); break;
+    case OPC_GEN_REGMUX(2, 1): lean_regmux<real, K, QGB_J(2), QGB_J(1)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(2, 3): if (K > 3) lean_regmux<real, K, QGB_J(2), QGB_J(3)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(3, 0): if (K > 3) lean_regmux<real, K, QGB_J(3), 0>(a, m, mo); break;
+    case OPC_GEN_REGMUX(3, 1): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(1)>(a, m, mo); break;
+    case OPC_GEN_REGMUX(3, 2): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(2)>(a, m, mo); break;
     case OPC_SWAP(0): lean_swap<real, K, 0>(a, op.regmask); break;
     case OPC_SWAP(1): lean_swap<real, K, QGB_J(1)>(a, op.regmask); break;
     case OPC_SWAP(2): lean_swap<real, K, QGB_J(2)>(a, op.regmask); break;
@@ -279,15 +294,15 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
     case OPC_DIAG_REG: {
         const uint32_t regmask = op.regmask, regsel = op.regsel;
         real d0r, d0i, d1r, d1i;
-        MatLayout<real>::factor(mo, 0, d0r, d0i);
-        MatLayout<real>::factor(mo, 1, d1r, d1i);
+        m.factor(0, d0r, d0i); /* register-bit diagonals have no thread / tile selector: mm == mo */
+        m.factor(1, d1r, d1i);
         lean_phase<K>(a, d0r, d0i, regmask & ~regsel);
         lean_phase<K>(a, d1r, d1i, regmask & regsel);
         break;
     }
     case OPC_DIAG_THR: {
         real dr, di;
-        MatLayout<real>::factor(mm, 0, dr, di); /* the selected block starts with the selected factor */
+        m.factor(0, dr, di); /* the selected block starts with the selected factor */
         lean_phase<K>(a, dr, di, op.regmask);
         break;
     }
