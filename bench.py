@@ -54,7 +54,8 @@ def parse_args():
     ap.add_argument('--depth', type=int, default=200)
     ap.add_argument('--dtype', default='f64', choices=('f64', 'f32'))
     ap.add_argument('--seed', type=int, default=1234)
-    ap.add_argument('--cpu-sample-gates', type=int, default=6)
+    ap.add_argument('--cpu-sample-gates', type=int, default=45,
+                    help='gates of layer 0 the CPU reference runs per step (45 = the whole layer at 30 qubits, ~12 s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--option', action='append', default=[], help='engine option name=value')
