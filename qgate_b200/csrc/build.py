@@ -19,6 +19,8 @@ SOURCES = ['engine.cu', 'dist.cu', 'kernels_tile.cu', 'kernels_tma.cu', 'kernels
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC,-Wall,-Wno-unused-function', '-Xptxas', '-v']
+if os.environ.get('QGB_PHASE_TIMING'):      # diagnostic build: per-phase cycle counters in the pass kernel
+    FLAGS.append('-DQGB_PHASE_TIMING')
 
 
 def _newest_header():

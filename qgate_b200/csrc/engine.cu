@@ -200,8 +200,8 @@ struct Options {
     int64_t fuse = 1;
     int64_t merge = 1;
     int64_t tile_lanes_fp64 = 11, tile_lanes_fp32 = 12;
-    /* low contiguous lanes forced into every tile; 0 = by staging engine: the 128-byte row of the
-     * TMA tensor map (3 complex128 / 4 complex64), 5 / 6 for the cp.async kernel's coalescing */
+    /* low contiguous lanes forced into every tile; 0 = 5 complex128 / 6 complex64 (512-byte runs);
+     * the TMA kernel needs at least the 128-byte row of its tensor map (3 / 4) */
     int64_t low_lanes_fp64 = 0, low_lanes_fp32 = 0;
     int64_t max_gates_per_pass = QGB_MAX_OPS;
     /* cap on the summed op cost of a pass (dense 2x2 = 4, diagonal / swap = 1); 0 = 32 for
@@ -291,7 +291,9 @@ void flush_tiled(QStates *qs) {
     cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     const int low_opt = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
-    const int low_auto = g.opt.tma != 0 ? (fp32 ? 4 : 3) : (fp32 ? 6 : 5);
+    /* runs of 512 bytes: a pass with few ops is HBM-bound and 128-byte runs (the TMA minimum) cost
+     * 27% of the DRAM bandwidth (5.95 vs 7.83 ms per complex128 pass at 30 qubits, profiles/r1za) */
+    const int low_auto = fp32 ? 6 : 5;
     cfg.L = low_opt > 0 ? low_opt : low_auto;
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
     const bool tma = g.opt.tma != 0;
@@ -1266,6 +1268,7 @@ int qgb_pool_delete(qgb_handle pool) {
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 
 int qgb_stats_get(qgb_stats *out) {
+    tma_pass_phase_report(); /* diagnostic builds only */
     *out = g.stats;
     return QGB_OK;
 }
@@ -1294,6 +1297,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "tma") g.opt.tma = value;
     else if (k == "tma_buffers") g.opt.tma_buffers = value;
     else if (k == "reg_bits_fp64") g.opt.reg_bits_fp64 = value;
+    else if (k == "tma_ws") tma_pass_set_warp_specialised((int)value);
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH
 }

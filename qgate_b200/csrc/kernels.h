@@ -49,6 +49,8 @@ cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf,
 /* shared memory of one CTA: n_buf tiles, the matrices of n_ops ops, n_stages thread tables */
 size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops);
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);
+void tma_pass_set_warp_specialised(int on); /* 1: a producer warp owns the TMA traffic (default 0) */
+void tma_pass_phase_report(); /* no-op unless built with -DQGB_PHASE_TIMING */
 
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
                                uint64_t ctrl_mask, uint64_t zero_mask, cudaStream_t stream);

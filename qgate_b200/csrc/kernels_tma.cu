@@ -22,6 +22,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 #include "kernels.h"
 #include "tile_ops.cuh"
 
@@ -35,6 +37,8 @@ struct TmaGeometry {
     uint32_t mask[QGB_MAX_GROUPS];   /* (1 << grp_r) - 1                                       */
     int32_t tbits[QGB_MAX_GROUPS];   /* coordinate = rest bits << tbits                        */
     int32_t base_shift[QGB_MAX_GROUPS]; /* lane of the group's first non-tile lane            */
+    unsigned long long *phase;       /* QGB_PHASE_TIMING=1: cycles per phase, summed over warp 0 of */
+                                     /* every CTA (diagnostic build only, see tma_pass_phase_report) */
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,6 +49,13 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+/* barrier among the first `count` threads of the CTA (a multiple of 32): the consumer warps */
+__device__ __forceinline__ void named_sync(uint32_t count) {
+    asm volatile("bar.sync 1, %0;\n" ::"r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -310,8 +321,17 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
     }
 }
 
-/* Shared memory: [NBUF tiles, 1024-byte aligned][NBUF mbarriers][per stage, per thread: base slot] */
-template <typename real, int K, int NT, int MINB, int NBUF>
+/* Shared memory: [NBUF tiles, 1024-byte aligned][2 NBUF mbarriers][matrices][per stage, per thread:
+ * base slot].
+ *
+ * WS (warp specialised, option tma_ws=1, tiles of >= 32 threads): the CTA has one extra PRODUCER
+ * warp that owns all TMA traffic — it stores a tile as soon as the consumers hand it over (`done`
+ * mbarrier), waits for the store to drain the buffer and refills it — so no computing thread
+ * waits for a store (thread 0 of the unspecialised kernel spends 27% of its time there, phase
+ * timing build).  Consumers synchronise among themselves on a named barrier.  Measured 5-7%
+ * SLOWER than the unspecialised kernel (the other resident CTAs already cover that wait, the
+ * extra warp costs registers): kept as an option, off by default. */
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
 __global__ void __launch_bounds__(NT, MINB)
 tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_constant__ CUtensorMap tmap,
                 const __grid_constant__ TmaGeometry geo) {
@@ -322,20 +342,23 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
     /* SWIZZLE_128B needs 1024-byte aligned tile buffers */
     unsigned char *tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t *full = reinterpret_cast<uint64_t *>(tiles + NBUF * tile_bytes);
+    uint64_t *done = full + NBUF; /* WS: consumers -> producer, "tile finished, writes fenced" */
     constexpr int MS = MatLayout<real>::kStride;
-    real *mats = reinterpret_cast<real *>(full + NBUF + (NBUF & 1)); /* 16-byte aligned: [op][m, m1][MS] */
+    real *mats = reinterpret_cast<real *>(full + 2 * NBUF); /* 16-byte aligned: [op][m, m1][MS] */
     uint32_t *lut = reinterpret_cast<uint32_t *>(mats + 2 * MS * prog.n_ops);
-    const uint32_t tid = threadIdx.x, nthr = blockDim.x; /* nthr == 2^(T-K) */
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nthr = WS ? blockDim.x - 32u : blockDim.x; /* computing threads == 2^(T-K) */
+    const bool producer = WS && tid >= nthr;
 
     /* the pass's matrices, once per CTA */
-    for (int i = tid; i < 2 * MS * prog.n_ops; i += nthr) {
+    for (int i = tid; !producer && i < 2 * MS * prog.n_ops; i += nthr) {
         const int o = i / (2 * MS), w = i - o * (2 * MS);
         const Op<real> &op = prog.op[o];
         mats[i] = w >= MS ? MatLayout<real>::slot(op.m1, w - MS) : MatLayout<real>::slot(op.m, w);
     }
 
     /* per stage: byte offset (inside a tile buffer) of this thread's base element */
-    for (int s = 0; s < prog.n_stages; ++s) {
+    for (int s = 0; !producer && s < prog.n_stages; ++s) {
         const Stage &st = prog.stage[s];
         uint32_t ebase = 0;
         for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
@@ -346,7 +369,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
      * matrix / factor (multiplexer or diagonal target on a thread bit): one bit per op, fixed
      * for the whole pass because a thread's elements do not depend on the tile. */
     uint32_t act = 0, sel_thr = 0; /* n_ops <= 32 */
-    for (int s = 0; s < prog.n_stages; ++s) {
+    for (int s = 0; !producer && s < prog.n_stages; ++s) {
         const Stage &st = prog.stage[s];
         uint32_t ebase = 0;
         for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
@@ -358,7 +381,10 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
     }
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        for (int b = 0; b < NBUF; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&done[b], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
@@ -384,17 +410,50 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         bulk_commit();
     };
 
-    /* prologue: the first tile */
-    if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+    if (WS) {
+        if (producer) {
+            if (tid == nthr) { /* one lane drives the TMA unit */
+                uint64_t t_load = blockIdx.x;
+                for (int j = 0; j < NBUF && t_load < n_tiles; ++j, t_load += stride) issue_load(t_load, j);
+                int pb = 0;
+                uint32_t pparity = 0;
+                for (uint64_t t = blockIdx.x; t < n_tiles; t += stride) {
+                    mbar_wait(&done[pb], pparity); /* the consumers are through with tile t */
+                    issue_store(t, pb);
+                    if (t_load < n_tiles) {
+                        bulk_wait_read<0>(); /* the store has drained the buffer: refill it */
+                        issue_load(t_load, pb);
+                        t_load += stride;
+                    }
+                    if (++pb == NBUF) {
+                        pb = 0;
+                        pparity ^= 1u;
+                    }
+                }
+                bulk_wait_read<0>(); /* shared memory stays alive until the last store has read it */
+            }
+            return;
+        }
+    } else {
+        /* prologue: the first tile */
+        if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+    }
 
     int b = 0;            /* buffer of the tile being worked on */
     uint32_t parity = 0;  /* phase of full[b] this tile completes */
+#ifdef QGB_PHASE_TIMING
+    long long ph_wait = 0, ph_load = 0, ph_ops = 0, ph_store = 0, ph_tail = 0, ph_t;
+#define PH_MARK(acc) do { const long long now_ = clock64(); acc += now_ - ph_t; ph_t = now_; } while (0)
+    ph_t = clock64();
+#else
+#define PH_MARK(acc) do { } while (0)
+#endif
     for (uint64_t t = blockIdx.x; t < n_tiles; t += stride) {
         /* prefetch the next tile into buffer b + 1.  That buffer held the tile stored NBUF - 1
          * iterations ago, so at most the newest NBUF - 2 stores may still be reading shared
          * memory (NBUF == 2: wait for the store just issued; NBUF == 3: load, stages and store
          * of three consecutive tiles overlap without a wait) */
-        if (tid == 0) {
+        if (!WS && tid == 0) {
             const uint64_t tn = t + stride;
             if (tn < n_tiles) {
                 bulk_wait_read<NBUF - 2>();
@@ -416,7 +475,9 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             if (lane >= 0 && ((base >> lane) & 1ull)) sel |= 1u << o;
         }
 
+        PH_MARK(ph_tail);
         mbar_wait(&full[b], parity);
+        PH_MARK(ph_wait);
         unsigned char *buf = tiles + (size_t)b * tile_bytes;
 
         for (int s = 0; s < prog.n_stages; ++s) {
@@ -437,6 +498,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             cplx a[1 << K];
 #pragma unroll
             for (int r = 0; r < (1 << K); ++r) a[r] = *reinterpret_cast<const cplx *>(buf + off[r]);
+            PH_MARK(ph_load);
 
             {
                 uint32_t bit = 1u << st.op_begin;
@@ -447,21 +509,43 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
                 }
             }
 
+            PH_MARK(ph_ops);
 #pragma unroll
             for (int r = 0; r < (1 << K); ++r) *reinterpret_cast<cplx *>(buf + off[r]) = a[r];
-            if (s + 1 < prog.n_stages) __syncthreads();
+            if (s + 1 < prog.n_stages) {
+                if (WS)
+                    named_sync(nthr);
+                else
+                    __syncthreads();
+            }
+            PH_MARK(ph_store);
         }
-        /* generic-proxy writes -> visible to the async proxy, then one thread stores the tile */
+        /* generic-proxy writes -> visible to the async proxy, then the tile goes back to HBM */
         fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) issue_store(t, b);
+        if (WS) {
+            named_sync(nthr);
+            if (tid == 0) mbar_arrive(&done[b]); /* the producer warp stores it */
+        } else {
+            __syncthreads();
+            if (tid == 0) issue_store(t, b);
+        }
 
         if (++b == NBUF) {
             b = 0;
             parity ^= 1u;
         }
     }
-    if (tid == 0) bulk_wait_read<0>();
+    if (!WS && tid == 0) bulk_wait_read<0>();
+#ifdef QGB_PHASE_TIMING
+    PH_MARK(ph_tail);
+    if (tid == 0 && geo.phase) {
+        atomicAdd(&geo.phase[0], (unsigned long long)ph_wait);
+        atomicAdd(&geo.phase[1], (unsigned long long)ph_load);
+        atomicAdd(&geo.phase[2], (unsigned long long)ph_ops);
+        atomicAdd(&geo.phase[3], (unsigned long long)ph_store);
+        atomicAdd(&geo.phase[4], (unsigned long long)ph_tail);
+    }
+#endif
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -469,6 +553,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn g_encode = nullptr;
+unsigned long long *g_phase = nullptr;
+int g_tma_ws = 0; /* measured 5-7% slower than the unspecialised kernel on B200 (profiles/r1z): off */
 int g_tma_sm_count = 148;
 int g_tma_max_smem = 48 * 1024;
 
@@ -495,6 +581,7 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     const uint64_t total_bytes = elem << prog.n_lanes;
     int consumed = 0;
     geo->n_groups = prog.n_groups;
+    geo->phase = g_phase;
     for (int d = 0; d < QGB_MAX_GROUPS; ++d) {
         if (d < prog.n_groups) {
             const int s = prog.grp_start[d], t = prog.grp_t[d], r = prog.grp_r[d];
@@ -525,17 +612,17 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <typename real, int K, int NT, int MINB, int NBUF>
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
 cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
                                size_t smem, cudaStream_t stream) {
     static int configured = 0;
-    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF>;
+    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF, WS>;
     if (!configured) {
         cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_max_smem);
         if (rc != cudaSuccess) return rc;
         configured = 1;
     }
-    const unsigned nthr = 1u << (prog.T - K);
+    const unsigned nthr = (1u << (prog.T - K)) + (WS ? 32u : 0u); /* + the producer warp */
     int per_sm = 0;
     cudaError_t rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)nthr, smem);
     if (rc != cudaSuccess) return rc;
@@ -558,15 +645,28 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
     if (rc != cudaSuccess) return rc;
     const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.K, prog.n_stages, n_buf, prog.n_ops);
     const int nthr = 1 << (prog.T - prog.K);
-    if (n_buf >= 3) {
-        if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 3>(prog, map, geo, smem, stream);
-        if (nthr <= 512) return launch_tma_variant<real, K, 512, 1, 3>(prog, map, geo, smem, stream);
-        return launch_tma_variant<real, K, 1024, 1, 3>(prog, map, geo, smem, stream);
+    (void)min_ctas;
+    if (!g_tma_ws) { /* A/B switch: the unspecialised kernel for every shape */
+        if (n_buf >= 3) {
+            if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 3, false>(prog, map, geo, smem, stream);
+            return launch_tma_variant<real, K, 1024, 1, 3, false>(prog, map, geo, smem, stream);
+        }
+        if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 2, false>(prog, map, geo, smem, stream);
+        return launch_tma_variant<real, K, 1024, 1, 2, false>(prog, map, geo, smem, stream);
     }
-    if (nthr <= 256 && min_ctas >= 3) return launch_tma_variant<real, K, 256, 3, 2>(prog, map, geo, smem, stream);
-    if (nthr <= 256) return launch_tma_variant<real, K, 256, 2, 2>(prog, map, geo, smem, stream);
-    if (nthr <= 512) return launch_tma_variant<real, K, 512, 1, 2>(prog, map, geo, smem, stream);
-    return launch_tma_variant<real, K, 1024, 1, 2>(prog, map, geo, smem, stream);
+    /* tiles of 32..512 computing threads: warp-specialised (one more warp per CTA) */
+    if (n_buf >= 3) {
+        if (nthr < 32) return launch_tma_variant<real, K, 256, 2, 3, false>(prog, map, geo, smem, stream);
+        if (nthr <= 128) return launch_tma_variant<real, K, 160, 3, 3, true>(prog, map, geo, smem, stream);
+        if (nthr <= 256) return launch_tma_variant<real, K, 288, 2, 3, true>(prog, map, geo, smem, stream);
+        if (nthr <= 512) return launch_tma_variant<real, K, 544, 1, 3, true>(prog, map, geo, smem, stream);
+        return launch_tma_variant<real, K, 1024, 1, 3, false>(prog, map, geo, smem, stream);
+    }
+    if (nthr < 32) return launch_tma_variant<real, K, 256, 2, 2, false>(prog, map, geo, smem, stream);
+    if (nthr <= 128) return launch_tma_variant<real, K, 160, 3, 2, true>(prog, map, geo, smem, stream);
+    if (nthr <= 256) return launch_tma_variant<real, K, 288, 2, 2, true>(prog, map, geo, smem, stream);
+    if (nthr <= 512) return launch_tma_variant<real, K, 544, 1, 2, true>(prog, map, geo, smem, stream);
+    return launch_tma_variant<real, K, 1024, 1, 2, false>(prog, map, geo, smem, stream);
 }
 
 } // namespace
@@ -576,10 +676,32 @@ size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int 
     size_t tiles = n_buf * (elem << T);
     tiles = (tiles + 1023) & ~(size_t)1023;
     /* + mbarriers, the matrices of up to QGB_MAX_OPS ops, the per-stage thread table, alignment slack */
-    return tiles + 8 * (n_buf + 1) + (prec == 1 ? 128 : 96) * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
+    return tiles + 16 * n_buf + (prec == 1 ? 128 : 96) * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
+}
+
+void tma_pass_set_warp_specialised(int on) { g_tma_ws = on ? 1 : 0; }
+
+/* Diagnostic (compile with -DQGB_PHASE_TIMING): where warp 0 of every CTA spends its cycles. */
+void tma_pass_phase_report() {
+#ifdef QGB_PHASE_TIMING
+    if (!g_phase) return;
+    unsigned long long h[5];
+    cudaMemcpy(h, g_phase, sizeof(h), cudaMemcpyDeviceToHost);
+    const double tot = (double)(h[0] + h[1] + h[2] + h[3] + h[4]);
+    if (tot > 0)
+        std::fprintf(stderr, "[qgb phase] wait-for-tile %.1f%%  stage loads %.1f%%  ops %.1f%%  stage stores+barrier %.1f%%  fence/store/issue %.1f%%\n",
+                     100. * h[0] / tot, 100. * h[1] / tot, 100. * h[2] / tot, 100. * h[3] / tot, 100. * h[4] / tot);
+    cudaMemset(g_phase, 0, sizeof(h));
+#endif
 }
 
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
+#ifdef QGB_PHASE_TIMING
+    if (!g_phase) {
+        cudaMalloc(&g_phase, 5 * sizeof(unsigned long long));
+        cudaMemset(g_phase, 0, 5 * sizeof(unsigned long long));
+    }
+#endif
     if (sm_count > 0) g_tma_sm_count = sm_count;
     g_tma_max_smem = max_smem_optin;
     return cudaSuccess;
