@@ -390,3 +390,24 @@ def test_errors_surface_as_exceptions(cuda_runtime):
     sim.run([S.H(q[0]), S.ctrl(q[0]).X(q[1])])
     with pytest.raises(RuntimeError):
         sim.run([S.reset(q[1])])   # not measured (rop_executor.py:45-51)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_simulator_sample_shot_for_shot(cuda_runtime, ref_runtime, dtype):
+    """Simulator.sample (simulator.py:85-119): every shot re-runs the circuit with dynamic qubit
+    grouping and one RNG draw per Measure; the observations equal the reference CPU runtime's."""
+    q = S.new_qregs(4)
+    refs = S.new_references(4)
+    ops = [S.H(q[0]), S.ctrl(q[0]).X(q[1]), S.Ry(0.7)(q[2]), S.ctrl(q[1]).Rx(1.1)(q[2]),
+           S.measure(refs[0], q[0]), S.measure(refs[1], q[1]), S.if_(refs[1], 1, S.X(q[2])),
+           S.ctrl(q[2]).H(q[3]), S.measure(refs[2], q[2]), S.reset(q[2]), S.H(q[2]),
+           S.measure(refs[3], q[3])]
+    outs = []
+    for rt in (cuda_runtime, ref_runtime.module):
+        sim = cases.make_sim(rt, dtype, 'dynamic')
+        np.random.seed(21)
+        outs.append(sim.sample(ops, refs, 200).intarray)
+        sim.terminate()
+    assert np.array_equal(outs[0], outs[1])
+    assert len(set(outs[0].tolist())) > 3

@@ -22,7 +22,9 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'tests
 MODULES = ['test_unary_gate', 'test_control_gate', 'test_calc_prob', 'test_measure', 'test_reset',
            'test_if', 'test_get_states', 'test_join', 'test_sampling_pool', 'test_swap_gate',
            'test_exp_gate', 'test_qreg_ordering', 'test_simple_calls',
-           'test_z_conv', 'test_big_circuits']
+           'test_z_conv', 'test_big_circuits', 'test_multidevice']
+# (test_sampling, test_U_gate, test_gate_matrix, test_repr, test_pauli_*, test_memstore generate no
+#  per-runtime ...CUDA classes: they exercise the reference's front end / py runtime only)
 
 
 @pytest.fixture(scope='module')
@@ -66,3 +68,34 @@ def test_reference_suite_on_our_runtime_objects(reference_with_our_runtime, modu
     problems = ['{}: {}'.format(t.id(), tb.splitlines()[-1]) for t, tb in result.errors + result.failures]
     assert not problems, '\n'.join(problems)
     assert result.testsRun > 0
+
+
+def test_simulator_sample_matches_reference_shot_for_shot(reference_with_our_runtime):
+    """`Simulator.sample` (simulator.py:85-119: the whole circuit re-run per shot, one global-RNG
+    draw per Measure): our front end on the oracle runtime and the real reference on its cpu
+    runtime return the same observation for every shot under the same seed."""
+    qgate = reference_with_our_runtime
+    import qgate_b200
+    import qgate_b200.script as S
+    from oracle import ref_runtime
+
+    def build(mod):
+        q = mod.new_qregs(3)
+        refs = mod.new_references(3)
+        ops = [mod.H(q[0]), mod.ctrl(q[0]).X(q[1]), mod.Ry(0.7)(q[2]), mod.ctrl(q[1]).Rx(1.1)(q[2]),
+               mod.measure(refs[0], q[0]), mod.measure(refs[1], q[1]),
+               mod.if_(refs[1], 1, mod.X(q[2])), mod.measure(refs[2], q[2])]
+        return refs, ops
+
+    import importlib
+    ref_script = importlib.import_module('qgate.script')
+    refs, ops = build(ref_script)
+    ref_sim = qgate.simulator.cpu(dtype=np.float64)
+    np.random.seed(5)
+    want = ref_sim.sample(ops, refs, 300).intarray
+    refs, ops = build(S)
+    sim = qgate_b200.simulator.with_runtime(ref_runtime.module, dtype=np.float64)
+    np.random.seed(5)
+    got = sim.sample(ops, refs, 300).intarray
+    assert np.array_equal(got, want)
+    assert len(set(got.tolist())) > 2
