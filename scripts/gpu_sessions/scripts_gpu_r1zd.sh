@@ -1,0 +1,17 @@
+#!/bin/bash
+# round-1 GPU session ZD: occupancy variants (more, smaller CTAs)
+mkdir -p gpurun_out
+Q="--steps 1 --warmup 1 --no-e2e --no-cpu-baseline --depth 60"
+show() { python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()[:300]); continue
+    r=d['roofline']; print('value %.3e passes %d gates/pass %.1f avg_ms %.2f GB/s %.0f frac %.3f clk %s'%(d['value'],r['launches_per_step'],r['gates_per_launch'],r['avg_launch_ms'],r['achieved'],r['frac'],d['clocks']['sm_mhz']))
+"; }
+for opt in "" "--option reg_bits_fp64=3 --option tile_lanes_fp64=10" "--option reg_bits_fp64=3 --option tile_lanes_fp64=10 --option max_cost=24" "--option tile_lanes_fp64=10" "--option tile_lanes_fp64=10 --option max_cost=24" "--option reg_bits_fp64=3"; do
+  echo "== f64 $opt"; timeout 200 python bench.py $Q $opt 2>&1 | show
+done
+for opt in "--option tile_lanes_fp32=11" "--option tile_lanes_fp32=11 --option tma_buffers=2"; do
+  echo "== f32 $opt"; timeout 200 python bench.py $Q --dtype f32 $opt 2>&1 | show
+done
