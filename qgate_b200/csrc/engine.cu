@@ -202,15 +202,15 @@ struct Options {
     /* complex128: 10-lane tiles (16 KiB, 64-thread CTAs, 6 per SM) overlap arithmetic and memory
      * traffic better than 11-lane ones: 0.72 vs 0.68 of the HBM roofline at the same pass cost
      * (profiles/r1z_pass_floor_and_sweeps.md) */
-    int64_t tile_lanes_fp64 = 10, tile_lanes_fp32 = 12;
+    int64_t tile_lanes_fp64 = 10, tile_lanes_fp32 = 11; /* 16 KiB tiles in both precisions */
     /* low contiguous lanes forced into every tile; 0 = 5 complex128 / 6 complex64 (512-byte runs);
      * the TMA kernel needs at least the 128-byte row of its tensor map (3 / 4) */
     int64_t low_lanes_fp64 = 0, low_lanes_fp32 = 0;
     int64_t max_gates_per_pass = QGB_MAX_OPS;
-    /* cap on the summed op cost of a pass (dense 2x2 = 4, diagonal / swap = 1); 0 = 24 for
-     * complex128 on the TMA kernel — 6 dense ops keep a pass above 70% of the HBM roofline; more
-     * ops per pass raise throughput by up to 12% and lower that fraction (profiles/r1z sweeps) —
-     * unlimited otherwise */
+    /* cap on the summed op cost of a pass (dense 2x2 = 4, diagonal / swap = 1); 0 = 24 on the TMA
+     * kernel — 6 dense ops keep a pass above 70% of the HBM roofline in both precisions; more ops
+     * per pass raise throughput by up to 18% and lower that fraction (profiles/r1z sweeps) —
+     * unlimited on the cp.async kernel */
     int64_t max_cost = 0;
     int64_t lookahead = 4096;
     int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
@@ -338,7 +338,7 @@ void flush_tiled(QStates *qs) {
         while (ms > 2 && smem_bytes(cfg.T, cfg.L, ms) > budget) --ms;
         cfg.max_stages = ms;
     }
-    cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : ((tma && !fp32) ? 24 : (1 << 30));
+    cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : (tma ? 24 : (1 << 30));
     cfg.lookahead = (int)g.opt.lookahead;
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
     PlanStats st;

@@ -26,7 +26,7 @@ PROB_TOL = {np.float64: 1e-12, np.float32: 2e-6}
 @pytest.fixture(autouse=True)
 def default_options(cuda_runtime):
     api = cuda_runtime.get_api()
-    for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 12),
+    for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 11),
                         ('low_lanes_fp64', 0), ('low_lanes_fp32', 0), ('max_gates_per_pass', 112), ('max_cost', 0),
                         ('tma', 1), ('tma_buffers', 0), ('tile_buffers', 1), ('reg_bits_fp64', 4),
                         ('ctas_per_sm', 0), ('tma_ws', 0)):
