@@ -279,7 +279,7 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
 
 template <typename real>
 static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops, int max_stages,
-                     bool merge, uint64_t seed, bool tma = false) {
+                     bool merge, uint64_t seed, bool tma = false, int reg_bits = 0, int max_cost = 0) {
     std::mt19937_64 rng(seed);
     std::vector<cd> ref(1ull << n), amp;
     std::normal_distribution<double> nd;
@@ -294,7 +294,8 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     }
     PlanConfig cfg;
     cfg.fp32 = sizeof(real) == 4;
-    cfg.K = cfg.fp32 ? 4 : 3;
+    cfg.K = reg_bits > 0 ? reg_bits : (cfg.fp32 ? 4 : 3);
+    if (max_cost > 0) cfg.max_cost = max_cost;
     cfg.T = T;
     cfg.L = L;
     cfg.max_ops = max_ops;
@@ -350,6 +351,13 @@ int main() {
                 run_case<float>(n, std::max(T, 9), L, 80, 2, QGB_MAX_OPS, QGB_MAX_STAGES, true, seed++, true);
             }
         }
+    }
+    /* the engine's defaults: 16 amplitudes per thread in both precisions, 16 KiB tiles, at most 32
+     * ops and a summed cost of 24 per pass */
+    for (int n : {10, 12, 14}) {
+        run_case<double>(n, 10, 5, 300, 3, 32, QGB_MAX_STAGES, true, seed++, true, 4, 24);
+        run_case<double>(n, 11, 3, 300, 9, 32, QGB_MAX_STAGES, true, seed++, true, 4, 32);
+        run_case<float>(n, 11, 6, 120, 3, 32, QGB_MAX_STAGES, true, seed++, true, 4, 24);
     }
     g_expect_tma = false;
     /* limits and no-merge paths */
