@@ -217,6 +217,8 @@ struct Options {
     int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
     int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
     int64_t tma = 1;               /* 1: TMA tensor-map staging (kernels_tma.cu), 0: cp.async */
+    int64_t warp_local = 0;        /* TMA kernel: warp instead of CTA barriers between stages where the */
+                                   /* planner can arrange it (correct, measured neutral: off)           */
     int64_t reg_bits_fp64 = 4;     /* amplitudes per thread = 2^this (TMA kernel: 3 or 4)     */
     int64_t tma_buffers = 0;       /* tile buffers per CTA of the TMA kernel: 2, 3, 0 = 2 for  */
                                    /* complex128, 3 for complex64 (measured best, profiles/)  */
@@ -322,6 +324,7 @@ void flush_tiled(QStates *qs) {
     int want_ctas_tma = 3;
     cfg.max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, QGB_MAX_OPS));
     if (tma) cfg.max_ops = std::min(cfg.max_ops, tma_ops);
+    cfg.warp_local = tma && g.opt.warp_local != 0;
     {
         /* stages: each costs a per-thread table entry in shared memory; keep the CTA small enough
          * for the occupancy its launch bounds ask for */
@@ -1301,6 +1304,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "tma") g.opt.tma = value;
     else if (k == "tma_buffers") g.opt.tma_buffers = value;
     else if (k == "reg_bits_fp64") g.opt.reg_bits_fp64 = value;
+    else if (k == "warp_local") g.opt.warp_local = value;
     else if (k == "tma_ws") tma_pass_set_warp_specialised((int)value);
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH

@@ -513,7 +513,9 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
 #pragma unroll
             for (int r = 0; r < (1 << K); ++r) *reinterpret_cast<cplx *>(buf + off[r]) = a[r];
             if (s + 1 < prog.n_stages) {
-                if (WS)
+                if (st.warp_local)
+                    __syncwarp(); /* the next stage reads only what this warp wrote (planner.cpp) */
+                else if (WS)
                     named_sync(nthr);
                 else
                     __syncthreads();

@@ -53,9 +53,14 @@ inline int bank_class(int tile_bit, bool fp32) {
     return -1;
 }
 
-void choose_thread_bits(const int8_t *R, int K, int T, bool fp32, int8_t *W) {
+/* Thread bits of a stage: the lane bits (thread bits 0..4) first, chosen by shared-memory bank
+ * class, then the rest.  `forced_high` (a mask of tile bits, none of them a register bit) is
+ * placed LAST: those become the warp-index bits. */
+void choose_thread_bits(const int8_t *R, int K, int T, bool fp32, int8_t *W, uint32_t forced_high = 0) {
     bool used[QGB_MAX_TILE_LANES] = {false};
     for (int j = 0; j < K; ++j) used[R[j]] = true;
+    for (int b = 0; b < T; ++b)
+        if (forced_high & (1u << b)) used[b] = true;
     int n_classes = fp32 ? 4 : 3;
     int n = 0;
     for (int c = 0; c < n_classes; ++c)
@@ -67,6 +72,8 @@ void choose_thread_bits(const int8_t *R, int K, int T, bool fp32, int8_t *W) {
             }
     for (int b = 0; b < T; ++b)
         if (!used[b]) W[n++] = (int8_t)b;
+    for (int b = 0; b < T; ++b)
+        if (forced_high & (1u << b)) W[n++] = (int8_t)b;
     for (; n < QGB_MAX_TILE_LANES; ++n) W[n] = 0;
 }
 
@@ -282,6 +289,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         for (int b = 0; b < T; ++b)
             if (used[b]) st.R[j++] = (int8_t)b;
         choose_thread_bits(st.R, K, T, cfg.fp32, st.W);
+        st.warp_local = 0;
         for (int r = 0; r < (1 << K); ++r) {
             uint32_t roff = 0;
             for (int jj = 0; jj < K; ++jj)
@@ -291,6 +299,33 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         for (int jj = 0; jj < QGB_MAX_REG_BITS; ++jj)
             st.xb[jj] = jj < K ? tile_swizzle(1u << st.R[jj], cfg.fp32) * (uint32_t)(2 * sizeof(real)) : 0u;
         st.op_begin = st.op_end = 0;
+    }
+    /* Warp-local stage transitions: a run of consecutive stages whose register bits leave at
+     * least (T - K - 5) tile bits untouched gets those bits as its warp-index bits.  Every warp
+     * then owns the same 2^(K+5) tile elements through the whole run. */
+    const int n_warp_bits = T - K - 5;
+    if (cfg.warp_local && n_warp_bits > 0 && (int)stageR.size() >= 2) {
+        const uint32_t tile_mask = (1u << T) - 1u;
+        std::vector<uint32_t> rmask(n_stages, 0u);
+        for (int s = 0; s < n_stages; ++s)
+            for (int j = 0; j < K; ++j) rmask[s] |= 1u << prog.stage[s].R[j];
+        int s = 0;
+        while (s < n_stages) {
+            uint32_t uni = rmask[s];
+            int e = s + 1;
+            while (e < n_stages && __builtin_popcount(~(uni | rmask[e]) & tile_mask) >= n_warp_bits) uni |= rmask[e++];
+            if (e - s >= 2) {
+                uint32_t forced = 0;
+                int need = n_warp_bits;
+                for (int b = T - 1; b >= 0 && need > 0; --b) /* the highest free bits: not bank-selecting */
+                    if (!((uni >> b) & 1u)) forced |= 1u << b, --need;
+                for (int i = s; i < e; ++i) {
+                    choose_thread_bits(prog.stage[i].R, K, T, cfg.fp32, prog.stage[i].W, forced);
+                    prog.stage[i].warp_local = i + 1 < e ? 1 : 0;
+                }
+            }
+            s = e;
+        }
     }
 
     /* ops, grouped by stage in pick order (pick order is stage-monotone) */

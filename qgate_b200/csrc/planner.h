@@ -22,6 +22,9 @@ struct PlanConfig {
      * most tensor-map groups a tile may need (0: any tile shape, cp.async staging) */
     int row_lanes = 0;
     int max_groups = 0;
+    /* give runs of consecutive stages the same warp-index bits (tile bits none of them uses as a
+     * register bit) so that a stage transition needs a warp barrier only (Stage::warp_local) */
+    bool warp_local = false;
 };
 
 struct PlanStats {

@@ -93,6 +93,10 @@ struct Stage {
     int16_t op_begin, op_end;
     int8_t R[QGB_MAX_REG_BITS];           /* register bit j  <-> tile bit R[j], ascending   */
     int8_t W[QGB_MAX_TILE_LANES];         /* thread bit i    <-> tile bit W[i]              */
+    int8_t warp_local;                    /* 1: the next stage reads only what the SAME warp   */
+                                          /* wrote in this one (identical warp-index bits and   */
+                                          /* the same union of lane + register bits): the TMA   */
+                                          /* kernel then synchronises the warp, not the CTA     */
     uint16_t sro[1 << QGB_MAX_REG_BITS];  /* swizzled tile offset of register index r       */
     uint32_t xb[QGB_MAX_REG_BITS];        /* swizzled BYTE offset of register bit j: the slot of */
                                           /* register r is base ^ XOR of xb[j] over the bits of r */

@@ -22,6 +22,7 @@ typedef std::complex<double> cd;
 
 static int g_failures = 0;
 static bool g_expect_tma = false;
+static long g_warp_local = 0;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
@@ -74,6 +75,34 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
             ++expect;
         }
         CHECK(expect == p.n_out, "%d out-of-tile references, expected %d", p.n_out, expect);
+    }
+    /* warp-local stage transitions: where a stage is flagged, the next stage's warps must own
+     * exactly the tile elements they owned in it (the kernel only synchronises the warp there) */
+    {
+        auto owner_map = [&](const Stage &st) {
+            std::vector<int> owner(tile_size, -1);
+            for (uint32_t tid = 0; tid < (1u << (T - K)); ++tid) {
+                uint32_t ebase = 0;
+                for (int i = 0; i < T - K; ++i) ebase |= ((tid >> i) & 1u) << st.W[i];
+                for (int r = 0; r < (1 << K); ++r) {
+                    uint32_t o = 0;
+                    for (int j = 0; j < K; ++j)
+                        if (r & (1 << j)) o |= 1u << st.R[j];
+                    owner[ebase | o] = (int)(tid >> 5);
+                }
+            }
+            return owner;
+        };
+        for (int s = 0; s + 1 < p.n_stages; ++s) {
+            if (!p.stage[s].warp_local) continue;
+            ++g_warp_local;
+            CHECK(T - K > 5, "warp-local flag on a single-warp tile");
+            const std::vector<int> a = owner_map(p.stage[s]), b = owner_map(p.stage[s + 1]);
+            bool same = true;
+            for (uint32_t e = 0; e < tile_size; ++e) same = same && a[e] == b[e] && a[e] >= 0;
+            CHECK(same, "stage %d is flagged warp-local but stage %d moves elements between warps", s, s + 1);
+        }
+        CHECK(p.stage[p.n_stages - 1].warp_local == 0, "the last stage must end with a CTA barrier");
     }
     std::vector<cd> tile(tile_size);
     if (g_expect_tma) CHECK(p.n_groups >= 1 && p.n_groups <= QGB_MAX_GROUPS, "tile does not fit a tensor map (%d groups)", p.n_groups);
@@ -300,6 +329,7 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     cfg.L = L;
     cfg.max_ops = max_ops;
     cfg.max_stages = max_stages;
+    cfg.warp_local = tma;
     if (tma) { /* what engine.cu sets for the TMA-staged kernel */
         cfg.row_lanes = cfg.fp32 ? 4 : 3;
         cfg.max_groups = QGB_MAX_GROUPS;
@@ -373,6 +403,11 @@ int main() {
                 g_mux_out);
     if (g_mux_thr == 0 || g_mux_reg == 0 || g_mux_out == 0) {
         std::printf("FAIL: a multiplexer placement was never exercised\n");
+        return 1;
+    }
+    std::printf("warp-local stage transitions checked: %ld\n", g_warp_local);
+    if (g_warp_local == 0) {
+        std::printf("FAIL: no warp-local stage transition was planned\n");
         return 1;
     }
     std::printf("ALL OK\n");

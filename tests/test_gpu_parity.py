@@ -29,7 +29,7 @@ def default_options(cuda_runtime):
     for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 11),
                         ('low_lanes_fp64', 0), ('low_lanes_fp32', 0), ('max_gates_per_pass', 112), ('max_cost', 0),
                         ('tma', 1), ('tma_buffers', 0), ('tile_buffers', 1), ('reg_bits_fp64', 4),
-                        ('ctas_per_sm', 0), ('tma_ws', 0)):
+                        ('ctas_per_sm', 0), ('tma_ws', 0), ('warp_local', 0)):
         api.set_option(name, value)
     yield
 
@@ -332,6 +332,9 @@ def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
         for t in (k + 5, k + 7, k + 8, k + 9):
             shapes.append({'fuse': 1, 'tma': 1, 'tma_ws': 1, 'tma_buffers': ws_buffers, lanes: t, low: 0})
     shapes.append({'fuse': 1, 'tma': 1, 'tma_ws': 0, 'tma_buffers': 0, lanes: k + 8, low: 0})
+    for t in (k + 6, k + 7, k + 8, k + 9):           # warp-local stage transitions
+        shapes.append({'fuse': 1, 'tma': 1, 'warp_local': 1, lanes: t, low: 0})
+    shapes.append({'fuse': 1, 'tma': 1, 'warp_local': 0, lanes: k + 6, low: 0})
     if dtype is np.float64:
         for t in (8, 9, 11, 12):
             shapes.append(dict(fuse=1, tma=1, tma_buffers=2, reg_bits_fp64=3, tile_lanes_fp64=t, low_lanes_fp64=5))
