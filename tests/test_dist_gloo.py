@@ -202,3 +202,19 @@ def test_joins_of_sharded_groups(world, ref_runtime):
         assert np.array_equal(got['bits'], want['bits'])
         assert got['stats']['sharded_joins'] >= 3 and got['stats']['gathered_operands'] >= 1, got['stats']
         assert got['stats']['sharded_joins'] >= 3 and got['stats']['gathered_operands'] >= 1, got['stats']
+
+
+def test_world_8_three_global_lanes(ref_runtime):
+    """g = 3 (the 8-GPU layout): 3-lane exchanges, rank predicates on three global lanes, pools and
+    readout over eight shards."""
+    results = _run_world(8, 'random', 'float64', 'one_static')
+    want = _expected('random', 'float64', 'one_static', 1234)
+    for rank, got in results.items():
+        assert got['sharded'] == 3
+        for key in ('states', 'slice', 'states_rev'):
+            assert np.abs(got[key] - want[key]).max() < 1e-12, (rank, key)
+        assert np.abs(got['p0'] - want['p0']).max() < 1e-12
+        for key in ('samples', 'samples_hidden', 'samples_empty'):
+            assert np.array_equal(got[key], want[key]), (rank, key)
+    assert results[0]['stats']['exchanges'] > 0
+    assert results[0]['stats']['exchange_lanes'] >= results[0]['stats']['exchanges']
