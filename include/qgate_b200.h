@@ -243,6 +243,8 @@ typedef struct qgb_stats {
     int64_t h2d_bytes;            /* host->device bytes moved by this library         */
     int64_t d2h_bytes;            /* device->host bytes moved by this library         */
     int64_t tma_passes;           /* tile passes staged by TMA tensor-map copies      */
+    int64_t shear_ops;            /* dense 2x2 gates applied as three in-place shears  */
+    int64_t direct_ops;           /* dense 2x2 gates applied as a direct 2x2 product   */
 } qgb_stats;
 int qgb_stats_get(qgb_stats *out);
 int qgb_stats_reset(void);

@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(os.path.dirname(HERE), 'lib')
 OBJ_DIR = os.path.join(HERE, 'build')
 LIB = os.path.join(LIB_DIR, 'libqgate_b200.so')
 
-SOURCES = ['engine.cu', 'dist.cu', 'kernels_tile.cu', 'kernels_tma.cu', 'kernels_ops.cu', 'planner.cpp', 'gate_matrix.cpp']
+SOURCES = ['engine.cu', 'dist.cu', 'kernels_tma.cu', 'kernels_ops.cu', 'planner.cpp', 'gate_matrix.cpp']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC,-Wall,-Wno-unused-function', '-Xptxas', '-v']

@@ -10,7 +10,7 @@
  * Design differences that matter:
  *   - apply_gate* only APPENDS to a per-qstates queue; any observer (probability, readout,
  *     collapse, join, synchronize, pool creation) flushes it through the planner into fused
- *     tile passes (planner.cpp, kernels_tile.cu).  The reference launches one kernel per gate.
+ *     tile passes (planner.cpp, kernels_tma.cu).  The reference launches one kernel per gate.
  *   - everything runs on one CUDA stream; the host blocks only where a value has to reach
  *     the host (calc_probability, get_states, sample, synchronize).
  *   - no CPU fallback of any kind: without a CUDA device every call fails with QGB_ERR_CUDA.
@@ -199,6 +199,10 @@ struct Pool {
 struct Options {
     int64_t fuse = 1;
     int64_t merge = 1;
+    /* 1: every gate as submitted, one kernel each, in the reference CPU runtime's arithmetic
+     * operation by operation (CPUQubitProcessor.cpp:316-324): amplitudes bit-identical to
+     * qgate.simulator.cpu's.  A verification mode (one state sweep per gate), off by default. */
+    int64_t exact = 0;
     /* complex128: 10-lane tiles (16 KiB, 64-thread CTAs, 6 per SM) overlap arithmetic and memory
      * traffic better than 11-lane ones: 0.72 vs 0.68 of the HBM roofline at the same pass cost
      * (profiles/r1z_pass_floor_and_sweeps.md) */
@@ -214,14 +218,19 @@ struct Options {
     int64_t max_cost = 0;
     int64_t lookahead = 4096;
     int64_t queue_limit = 1 << 16; /* flush when a queue grows past this many gates */
-    int64_t tile_buffers = 1;      /* 2: prefetch the next tile under the current one        */
     int64_t ctas_per_sm = 0;       /* smem budget: resident CTAs to aim for (0 = by shape)   */
-    int64_t tma = 1;               /* 1: TMA tensor-map staging (kernels_tma.cu), 0: cp.async */
+    /* dense gates as three in-place shears (program.h OP_SHEAR): 12 instead of 16 FMAs per pair */
+    int64_t shear_fp64 = 1, shear_fp32 = 1;
     int64_t warp_local = 0;        /* TMA kernel: warp instead of CTA barriers between stages where the */
                                    /* planner can arrange it (correct, measured neutral: off)           */
     int64_t reg_bits_fp64 = 4;     /* amplitudes per thread = 2^this (TMA kernel: 3 or 4)     */
     int64_t tma_buffers = 0;       /* tile buffers per CTA of the TMA kernel: 2, 3, 0 = 2 for  */
                                    /* complex128, 3 for complex64 (measured best, profiles/)  */
+    /* W > 0: sampling pools and marginal probabilities are built exactly as a reference CPU runtime
+     * with W worker threads builds them — running sums in the state precision, W sequential spans
+     * (CPUSamplingPool.cpp:13-47, CPUQubitsStatesGetter.cpp:179-247) — so that sampled indices are
+     * bit-identical to its for identical probabilities.  0: the parallel float64 scan. */
+    int64_t pool_compat_workers = 0;
 };
 
 struct Engine {
@@ -237,6 +246,8 @@ struct Engine {
     void *h_stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_done[2] = {nullptr, nullptr};
     size_t stage_bytes = size_t(32) << 20;
+    void *h_gather = nullptr;     /* pinned staging of readout lane tables */
+    size_t gather_bytes = 0;
     Options opt;
     qgb_stats stats;
     std::unordered_set<QStates *> qstates;
@@ -246,6 +257,10 @@ struct Engine {
 };
 
 Engine g;
+
+} // namespace
+void close_all_ipc_mappings(); /* defined next to the IPC entry points */
+namespace {
 
 void require_init() {
     if (!g.initialized) fail(QGB_ERR_RUNTIME, "devices are not initialized (call qgb_devices_initialize).");
@@ -288,12 +303,18 @@ void check_lane(const QStates *qs, int lane) {
 
 int min_tile_lanes(int prec) { return prec == QGB_PREC_FP64 ? 3 + 5 : 4 + 5; }
 
+/* cap on the summed op cost of a pass (sheared 2x2 = 3, direct 2x2 = 4, diagonal / exchange = 1) */
+int default_max_cost(bool fp32, bool shear) {
+    (void)fp32;
+    return shear ? 21 : 24;
+}
+
 template <typename real>
 void flush_tiled(QStates *qs) {
     const bool fp32 = sizeof(real) == 4;
     PlanConfig cfg;
     cfg.fp32 = fp32;
-    cfg.K = fp32 ? 4 : ((g.opt.tma != 0 && g.opt.reg_bits_fp64 == 4) ? 4 : 3);
+    cfg.K = fp32 ? 4 : (g.opt.reg_bits_fp64 == 3 ? 3 : 4);
     cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     const int low_opt = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
@@ -301,72 +322,58 @@ void flush_tiled(QStates *qs) {
      * 27% of the DRAM bandwidth (5.95 vs 7.83 ms per complex128 pass at 30 qubits, profiles/r1za) */
     const int low_auto = fp32 ? 6 : 5;
     cfg.L = low_opt > 0 ? low_opt : low_auto;
+    const int n_buf = g.opt.tma_buffers == 0 ? (fp32 ? 3 : 2) : (g.opt.tma_buffers >= 3 ? 3 : 2);
+    /* ops per pass: their matrices are staged in shared memory, their predicates are one bit each */
+    const int max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
-    const bool tma = g.opt.tma != 0;
-    const int tma_buf = g.opt.tma_buffers == 0 ? (fp32 ? 3 : 2) : (g.opt.tma_buffers >= 3 ? 3 : 2);
-    const int n_buf = tma ? tma_buf : (g.opt.tile_buffers == 2 ? 2 : 1);
-    /* ops per TMA pass: their matrices are staged in shared memory (8 complex per op) */
-    const int tma_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
-    auto smem_bytes = [&](int T, int L, int stages) {
-        return tma ? tma_pass_smem_bytes(qs->prec, T, cfg.K, stages, n_buf, tma_ops)
-                   : tile_pass_smem_bytes(qs->prec, T, L, stages, n_buf);
-    };
-    while (cfg.T > cfg.K + 5 && smem_bytes(cfg.T, 1, 8) > (size_t)g.max_smem_optin) --cfg.T;
+    while (cfg.T > cfg.K + 5 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, 8, n_buf, max_ops) > (size_t)g.max_smem_optin)
+        --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
     if (cfg.T >= qs->n_lanes) cfg.L = std::min(low_opt > 0 ? low_opt : low_auto, cfg.T);
-    if (tma) {
-        /* the 128-byte row of the tensor map lies inside every tile */
-        cfg.row_lanes = fp32 ? 4 : 3;
-        cfg.max_groups = QGB_MAX_GROUPS;
-        cfg.L = std::max(cfg.L, cfg.row_lanes);
-    }
-    int want_ctas_tma = 3;
-    cfg.max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, QGB_MAX_OPS));
-    if (tma) cfg.max_ops = std::min(cfg.max_ops, tma_ops);
-    cfg.warp_local = tma && g.opt.warp_local != 0;
+    /* the 128-byte row of the tensor map lies inside every tile */
+    cfg.row_lanes = fp32 ? 4 : 3;
+    cfg.max_groups = QGB_MAX_GROUPS;
+    cfg.L = std::max(cfg.L, cfg.row_lanes);
+    cfg.max_ops = max_ops;
+    cfg.warp_local = g.opt.warp_local != 0;
+    cfg.shear = (fp32 ? g.opt.shear_fp32 : g.opt.shear_fp64) != 0;
     {
         /* stages: each costs a per-thread table entry in shared memory; keep the CTA small enough
          * for the occupancy its launch bounds ask for */
         const int nthr = 1 << (cfg.T - cfg.K);
-        int want_ctas;
-        if (tma)
-            want_ctas = nthr <= 256 ? (n_buf == 3 ? 2 : 3) : 1;
-        if (tma && g.opt.ctas_per_sm > 0) want_ctas_tma = (int)g.opt.ctas_per_sm;
-        else
-            want_ctas = nthr <= 256 ? (n_buf == 2 ? 3 : 4) : (nthr <= 512 ? 2 : 1);
+        int want_ctas = nthr <= 256 ? (n_buf == 3 ? 2 : 3) : 1;
         if (g.opt.ctas_per_sm > 0) want_ctas = (int)g.opt.ctas_per_sm;
         const size_t budget = (size_t)(g.max_smem_optin + 1024) / want_ctas - 1024;
         int ms = QGB_MAX_STAGES;
-        while (ms > 2 && smem_bytes(cfg.T, cfg.L, ms) > budget) --ms;
+        while (ms > 2 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, ms, n_buf, max_ops) > budget) --ms;
         cfg.max_stages = ms;
     }
-    cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : (tma ? 24 : (1 << 30));
+    cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : default_max_cost(fp32, cfg.shear);
     cfg.lookahead = (int)g.opt.lookahead;
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
     PlanStats st;
     while (!qs->queue.empty()) {
         plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
         if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
-        if (tma && prog.n_groups >= 1) {
-            CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, want_ctas_tma, g.stream));
-            g.stats.tma_passes += 1;
-        } else {
-            if (tma && prog.K != (fp32 ? 4 : 3)) fail(QGB_ERR_RUNTIME, "planner produced a tile no tensor map describes.");
-            CUDA_CHECK(launch_tile_pass<real>(prog, qs->d_amp, tma ? 1 : n_buf, g.stream));
-        }
+        if (prog.n_groups < 1) fail(QGB_ERR_RUNTIME, "planner produced a tile no tensor map describes.");
+        CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, 3, g.stream));
+        g.stats.tma_passes += 1;
         g.stats.kernel_launches += 1;
         g.stats.tile_passes += 1;
         g.stats.h2d_bytes += (int64_t)sizeof(prog) + 256; /* the pass program travels as kernel parameters */
         g.stats.gates_executed += st.gates_in_pass;
         g.stats.pass_bytes += (int64_t)(2 * qs->bytes());
+        g.stats.shear_ops += st.shear_ops;
+        g.stats.direct_ops += st.direct_ops;
     }
 }
 
 void flush(QStates *qs) {
     if (qs->queue.empty()) return;
     check_allocated(qs);
-    if (g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec)) {
+    const bool exact = g.opt.exact != 0;
+    if (!exact && g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec)) {
         if (qs->prec == QGB_PREC_FP64)
             flush_tiled<double>(qs);
         else
@@ -376,13 +383,13 @@ void flush(QStates *qs) {
             if (gt.mux >= 0) {
                 /* multiplexed gate (host-side merging): m where lane mux is 0, m1 where it is 1 */
                 CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, 0,
-                                              1ull << gt.mux, g.stream));
+                                              1ull << gt.mux, false, g.stream));
                 CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m1, gt.target,
-                                              1ull << gt.mux, 0, g.stream));
+                                              1ull << gt.mux, 0, false, g.stream));
                 g.stats.kernel_launches += 1;
             } else {
                 CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, gt.ctrl_mask,
-                                              0, g.stream));
+                                              0, exact, g.stream));
             }
             g.stats.kernel_launches += 1;
             g.stats.gates_executed += 1;
@@ -404,7 +411,7 @@ void submit_gate(QStates *qs, const double *mat8, const int *ctrl, int n_ctrl, i
         gt.ctrl_mask |= 1ull << ctrl[i];
     }
     /* merging pays on the tiled path only; the one-kernel-per-gate path keeps the submitted gates */
-    const bool tiled = g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec);
+    const bool tiled = !g.opt.exact && g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec);
     enqueue_gate(qs->queue, gt, g.opt.merge != 0 && tiled);
     g.stats.gates_submitted += 1;
     g.stats.gate_amp_updates += (int64_t)1 << (qs->n_lanes - n_ctrl);
@@ -427,10 +434,23 @@ void free_qstates_buffer(QStates *qs) {
 
 /* ---- readout helpers ------------------------------------------------------------------------ */
 
+/* lane tables of a readout -> device memory (pinned staging, stream-ordered); the caller hands the
+ * device block back with release_gather once its kernels are queued */
 void build_gather(GatherParams &gp, int prec, const int *lane_tables, const int *n_per,
                   const qgb_handle *list, int n_qstates, int n_ext_lanes) {
-    if (n_qstates > QGB_MAX_QSTATES) fail(QGB_ERR_INVALID, "too many qstates (%d).", n_qstates);
+    if (n_qstates < 0) fail(QGB_ERR_INVALID, "negative number of qstates.");
     gp.n_qstates = n_qstates;
+    gp.qs = nullptr;
+    if (n_qstates == 0) return;
+    const size_t bytes = sizeof(LaneTable) * (size_t)n_qstates;
+    if (bytes > g.gather_bytes) {
+        stream_sync(); /* the old staging block may still be the source of a copy */
+        if (g.h_gather) CUDA_CHECK(cudaFreeHost(g.h_gather));
+        g.h_gather = nullptr;
+        g.gather_bytes = std::max<size_t>(2 * bytes, 64 * sizeof(LaneTable));
+        CUDA_CHECK(cudaMallocHost(&g.h_gather, g.gather_bytes));
+    }
+    LaneTable *host = static_cast<LaneTable *>(g.h_gather);
     const int *p = lane_tables;
     for (int q = 0; q < n_qstates; ++q) {
         QStates *qs = QS(list[q]);
@@ -440,41 +460,63 @@ void build_gather(GatherParams &gp, int prec, const int *lane_tables, const int 
             fail(QGB_ERR_INVALID, "lane table of qstates %d has %d entries, expected %d.", q, n_per[q],
                  qs->n_lanes);
         flush(qs);
-        gp.qs[q].amp = qs->d_amp;
-        gp.qs[q].n_lanes = qs->n_lanes;
+        host[q].amp = qs->d_amp;
+        host[q].n_lanes = qs->n_lanes;
         for (int l = 0; l < qs->n_lanes; ++l) {
             if (p[l] < 0 || p[l] >= n_ext_lanes)
                 fail(QGB_ERR_INVALID, "external lane %d out of range [0, %d).", p[l], n_ext_lanes);
-            gp.qs[q].ext[l] = (int8_t)p[l];
+            host[q].ext[l] = (int8_t)p[l];
         }
         p += n_per[q];
     }
+    void *dev = g.pool.alloc(bytes);
+    gp.qs = static_cast<const LaneTable *>(dev);
+    CUDA_CHECK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, g.stream));
+    g.stats.h2d_bytes += (int64_t)bytes;
 }
 
-/* marginal probability vector on the device, 2^n_lanes doubles (caller releases to the pool) */
+void release_gather(GatherParams &gp) {
+    if (gp.qs) g.pool.release(const_cast<LaneTable *>(gp.qs));
+    gp.qs = nullptr;
+}
+
+/* marginal probability vector on the device, 2^n_lanes doubles (caller releases to the pool).
+ * Default: hidden lanes summed in double, 8 lanes per level.  compat (option pool_compat_workers):
+ * the reference CPU runtime's own levels and precision — 4 lanes per level, running sums in the
+ * state precision (CPUQubitsStatesGetter.cpp:179-247). */
 double *device_prob_array(int prec, const int *lane_tables, const int *n_per, const qgb_handle *list,
                           int n_qstates, int n_lanes, int n_hidden) {
-    if (n_lanes < 0 || n_hidden < 0 || n_lanes + n_hidden > QGB_MAX_LANES)
+    if (n_lanes < 0 || n_hidden < 0 || n_lanes > QGB_MAX_LANES || n_lanes + n_hidden > 62)
         fail(QGB_ERR_INVALID, "bad lane counts (%d, %d).", n_lanes, n_hidden);
+    const bool compat = g.opt.pool_compat_workers > 0;
+    const int per_level = compat ? 4 : 8;
     GatherParams gp;
     build_gather(gp, prec, lane_tables, n_per, list, n_qstates, n_lanes + n_hidden);
-    /* level 0 sums at most 8 hidden lanes per thread, the rest is folded 8 lanes at a time */
-    int h0 = std::min(n_hidden, 8);
-    int rest = n_hidden - h0;
-    int64_t count = (int64_t)1 << (n_lanes + rest);
-    double *cur = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
-    CUDA_CHECK(launch_prob_array(prec, cur, gp, h0, 0, count, g.stream));
-    g.stats.kernel_launches += 1;
-    while (rest > 0) {
-        const int h = std::min(rest, 8);
-        rest -= h;
-        count = (int64_t)1 << (n_lanes + rest);
-        double *next = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
-        CUDA_CHECK(launch_reduce_groups(next, cur, h, count, g.stream));
+    double *cur = nullptr;
+    try {
+        int h0 = std::min(n_hidden, per_level);
+        int rest = n_hidden - h0;
+        int64_t count = (int64_t)1 << (n_lanes + rest);
+        cur = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
+        CUDA_CHECK(launch_prob_array(prec, cur, gp, h0, 0, count, compat, g.stream));
         g.stats.kernel_launches += 1;
-        g.pool.release(cur);
-        cur = next;
+        while (rest > 0) {
+            const int h = std::min(rest, per_level);
+            rest -= h;
+            count = (int64_t)1 << (n_lanes + rest);
+            double *next = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)count));
+            cudaError_t rc = launch_reduce_groups(next, cur, h, count, compat && prec == QGB_PREC_FP32, g.stream);
+            g.pool.release(cur);
+            cur = next;
+            CUDA_CHECK(rc);
+            g.stats.kernel_launches += 1;
+        }
+    } catch (...) {
+        release_gather(gp);
+        if (cur) g.pool.release(cur);
+        throw;
     }
+    release_gather(gp);
     return cur;
 }
 
@@ -529,7 +571,6 @@ int qgb_devices_initialize(const int *device_ids, int n_device_ids, int max_po2i
     CUDA_CHECK(cudaDeviceGetAttribute(&g.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CUDA_CHECK(cudaStreamCreateWithFlags(&g.own_stream, cudaStreamNonBlocking));
     g.stream = g.own_stream;
-    CUDA_CHECK(tile_pass_configure(g.max_smem_optin, g.sm_count));
     CUDA_CHECK(tma_pass_configure(g.max_smem_optin, g.sm_count));
     g.pool.budget = memory_store_size;
     CUDA_CHECK(cudaMalloc(&g.d_partials, sizeof(double) * 4096));
@@ -554,7 +595,11 @@ int qgb_devices_clear(void) {
         qs->n_lanes = -1;
     }
     for (Pool *p : g.pools) p->d_cum = p->d_sums = nullptr;
+    close_all_ipc_mappings();
     g.pool.clear();
+    if (g.h_gather) cudaFreeHost(g.h_gather);
+    g.h_gather = nullptr;
+    g.gather_bytes = 0;
     cudaFree(g.d_partials);
     cudaFreeHost(g.h_scalar);
     cudaFree(g.d_stage);
@@ -810,6 +855,16 @@ struct IpcMapping {
 std::map<std::string, IpcMapping> g_ipc_open;
 } // namespace
 
+} /* extern "C" */
+namespace qgb {
+void close_all_ipc_mappings() {
+    for (auto &kv : g_ipc_open) cudaIpcCloseMemHandle(kv.second.base);
+    g_ipc_open.clear();
+    cudaGetLastError();
+}
+} // namespace qgb
+extern "C" {
+
 int qgb_qstates_ipc_export(qgb_handle h, void *handle64, int64_t *offset) {
     QGB_TRY
     require_init();
@@ -1025,15 +1080,15 @@ int qgb_getter_get_states(qgb_handle getter, void *array, int64_t array_offset, 
     Getter *gt = QG(getter);
     /* range checks of glue.cpp:465-478 */
     if (n_ext_lanes < 0 || n_ext_lanes > 62) fail(QGB_ERR_INVALID, "value out of range");
+    if (mathop != QGB_MATHOP_NULL && mathop != QGB_MATHOP_PROB) fail(QGB_ERR_RUNTIME, "unknown math op.");
+    if (n_states <= 0) return QGB_OK; /* nothing to read: no range to check */
     const int64_t space = (int64_t)1 << n_ext_lanes;
     if (start < 0 || space <= start) fail(QGB_ERR_INVALID, "value out of range");
     const int64_t end = start + step * (n_states - 1);
     if (end < 0 || space <= end) fail(QGB_ERR_INVALID, "value out of range");
-    if (mathop != QGB_MATHOP_NULL && mathop != QGB_MATHOP_PROB) fail(QGB_ERR_RUNTIME, "unknown math op.");
     const size_t real_size = gt->prec == QGB_PREC_FP64 ? 8 : 4;
     const size_t item = (mathop == QGB_MATHOP_NULL) ? 2 * real_size : real_size;
     char *dst = static_cast<char *>(array) + array_offset * item;
-    if (n_states <= 0) return QGB_OK;
     if (n_qstates == 0) {
         /* no qstates at all: |0...0> (glue.cpp:481-496) — a host-side constant, no device work */
         std::memset(dst, 0, (size_t)n_states * item);
@@ -1062,6 +1117,7 @@ int qgb_getter_get_states(qgb_handle getter, void *array, int64_t array_offset, 
         g.stats.d2h_bytes += pending_count[b] * (int64_t)item;
         pending_count[b] = 0;
     };
+    try {
     while (done < n_states) {
         const int64_t count = std::min(per_chunk, n_states - done);
         drain(buf);
@@ -1079,6 +1135,11 @@ int qgb_getter_get_states(qgb_handle getter, void *array, int64_t array_offset, 
     }
     drain(buf);
     drain(buf ^ 1);
+    } catch (...) {
+        release_gather(gp);
+        throw;
+    }
+    release_gather(gp);
     QGB_CATCH
 }
 
@@ -1130,6 +1191,62 @@ static void pool_scan_finalize(Pool *p, double offset, double total) {
     p->finalized = true;
 }
 
+} /* extern "C" */
+/* The reference-compatible build (option pool_compat_workers = W): W sequential spans in the state
+ * precision V, span totals prefix-summed in V on the host (W values), then (p + offset) * (V(1) / sum)
+ * — CPUSamplingPool.cpp:13-47, Parallel.h:12-23, Parallel.cpp:60-67 (one worker up to 2^16 entries).
+ * Returns the total the reference checks against 1. */
+template <typename V>
+static double pool_scan_compat(Pool *p, int workers) {
+    const int64_t n = (int64_t)1 << p->n_lanes;
+    const int w = n > ((int64_t)1 << 16) ? workers : 1;
+    int64_t span = (n + w - 1) / w;
+    span = ((span + 15) / 16) * 16;
+    if (w > 2048) fail(QGB_ERR_INVALID, "pool_compat_workers is limited to 2048.");
+    double *d_tot = g.d_partials; /* 4096 doubles: totals in [0, w), offsets in [2048, 2048 + w) */
+    CUDA_CHECK(launch_compat_scan(p->prec, p->d_cum, n, span, w, d_tot, g.stream));
+    std::vector<double> tot((size_t)w);
+    CUDA_CHECK(cudaMemcpyAsync(tot.data(), d_tot, sizeof(double) * (size_t)w, cudaMemcpyDeviceToHost, g.stream));
+    stream_sync();
+    V v = V(0);
+    for (int i = 0; i < w; ++i) { /* CPUSamplingPool.cpp:26-30 */
+        v += (V)tot[(size_t)i];
+        tot[(size_t)i] = (double)v;
+    }
+    const V sum = v;
+    if (0.05 < std::abs(sum - V(1.))) return (double)sum; /* the caller raises (CPUSamplingPool.cpp:31-34) */
+    const V norm = V(1.) / sum;
+    CUDA_CHECK(cudaMemcpyAsync(d_tot + 2048, tot.data(), sizeof(double) * (size_t)w, cudaMemcpyHostToDevice, g.stream));
+    CUDA_CHECK(launch_compat_apply(p->prec, p->d_cum, n, span, d_tot + 2048, (double)norm, g.stream));
+    stream_sync(); /* `tot` is the source of an asynchronous copy */
+    g.stats.kernel_launches += 2;
+    g.stats.d2h_bytes += (int64_t)sizeof(double) * w;
+    p->finalized = true;
+    return (double)sum;
+}
+extern "C" {
+
+static void pool_destroy(Pool *p);
+static void pool_check_total(Pool *p, double total);
+
+/* scan + normalise the marginal vector in p->d_cum; destroys the pool and raises on a bad total */
+static void pool_build(Pool *p) {
+    try {
+        if (g.opt.pool_compat_workers > 0) {
+            const int w = (int)std::min<int64_t>(g.opt.pool_compat_workers, 1 << 20);
+            const double total = p->prec == QGB_PREC_FP64 ? pool_scan_compat<double>(p, w) : pool_scan_compat<float>(p, w);
+            pool_check_total(p, total);
+            return;
+        }
+        const double total = pool_scan_partial(p);
+        pool_check_total(p, total);
+        pool_scan_finalize(p, 0., total);
+    } catch (...) {
+        if (g.pools.count(p)) pool_destroy(p);
+        throw;
+    }
+}
+
 static void pool_set_empty_lanes(Pool *p, const int *empty_lanes, int n_empty) {
     if (n_empty < 0 || n_empty > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of empty lanes.");
     std::vector<int> sorted(empty_lanes, empty_lanes + n_empty);
@@ -1142,6 +1259,7 @@ static void pool_set_empty_lanes(Pool *p, const int *empty_lanes, int n_empty) {
 }
 
 static void pool_destroy(Pool *p) {
+    if (!g.pools.count(p)) return;
     if (p->d_cum) g.pool.release(p->d_cum);
     if (p->d_sums) g.pool.release(p->d_sums);
     g.pools.erase(p);
@@ -1175,9 +1293,7 @@ int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, c
         pool_destroy(p);
         throw;
     }
-    const double total = pool_scan_partial(p);
-    pool_check_total(p, total);
-    pool_scan_finalize(p, 0., total);
+    pool_build(p);
     *out = reinterpret_cast<qgb_handle>(p);
     QGB_CATCH
 }
@@ -1199,7 +1315,12 @@ int qgb_getter_create_sampling_pool_partial(qgb_handle getter, const int *lane_t
         pool_destroy(p);
         throw;
     }
-    *local_total = pool_scan_partial(p);
+    try {
+        *local_total = pool_scan_partial(p);
+    } catch (...) {
+        pool_destroy(p);
+        throw;
+    }
     *out = reinterpret_cast<qgb_handle>(p);
     QGB_CATCH
 }
@@ -1234,9 +1355,7 @@ int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes, const in
         pool_destroy(p);
         throw;
     }
-    const double total = pool_scan_partial(p);
-    pool_check_total(p, total);
-    pool_scan_finalize(p, 0., total);
+    pool_build(p);
     *out = reinterpret_cast<qgb_handle>(p);
     QGB_CATCH
 }
@@ -1290,6 +1409,7 @@ int qgb_set_option(const char *name, int64_t value) {
     const std::string k(name ? name : "");
     if (k == "fuse") g.opt.fuse = value;
     else if (k == "merge") g.opt.merge = value;
+    else if (k == "exact") g.opt.exact = value;
     else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
     else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;
     else if (k == "low_lanes_fp64") g.opt.low_lanes_fp64 = value;
@@ -1299,12 +1419,17 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "max_cost") g.opt.max_cost = value;
     else if (k == "lookahead") g.opt.lookahead = value;
     else if (k == "queue_limit") g.opt.queue_limit = value;
-    else if (k == "tile_buffers") g.opt.tile_buffers = value;
+    else if (k == "tile_buffers" || k == "tma") { /* accepted for old scripts: TMA staging is the only path */ }
     else if (k == "ctas_per_sm") g.opt.ctas_per_sm = value;
-    else if (k == "tma") g.opt.tma = value;
+    else if (k == "shear") g.opt.shear_fp64 = g.opt.shear_fp32 = value;
+    else if (k == "shear_fp64") g.opt.shear_fp64 = value;
+    else if (k == "shear_fp32") g.opt.shear_fp32 = value;
+    else if (k == "l2_hint") tma_pass_set_l2_hint((int)value);
+    else if (k == "debug_pass_mode") tma_pass_set_debug_mode((int)value);
     else if (k == "tma_buffers") g.opt.tma_buffers = value;
     else if (k == "reg_bits_fp64") g.opt.reg_bits_fp64 = value;
     else if (k == "warp_local") g.opt.warp_local = value;
+    else if (k == "pool_compat_workers") g.opt.pool_compat_workers = value;
     else if (k == "tma_ws") tma_pass_set_warp_specialised((int)value);
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH

@@ -1,5 +1,5 @@
 /*
- * kernels.h — launchers of the sm_100a kernels (definitions in kernels_tile.cu, kernels_ops.cu).
+ * kernels.h — launchers of the sm_100a kernels (definitions in kernels_tma.cu, kernels_ops.cu, dist.cu).
  * Every launcher enqueues on `stream` and returns the cudaError_t of the launch; none of
  * them synchronises.  `prec` is QGB_PREC_FP64 (1) or QGB_PREC_FP32 (2); amplitudes are
  * interleaved (re, im) in that precision.
@@ -12,7 +12,7 @@
 
 namespace qgb {
 
-/* maximum number of qstates multiplied together by one get_states / prob-array launch */
+/* maximum number of source qstates of one join (the product has at least that many lanes) */
 #define QGB_MAX_QSTATES 40
 
 struct SortedBits {
@@ -27,21 +27,15 @@ struct LaneTable {
     int8_t ext[QGB_MAX_LANES];
 };
 
+/* any number of qstates (dynamic qubit grouping keeps every unentangled qreg as its own 1-lane
+ * qstates): the tables live in device memory */
 struct GatherParams {
     int32_t n_qstates;
-    LaneTable qs[QGB_MAX_QSTATES];
+    const LaneTable *qs; /* device array of n_qstates tables */
 };
 
 /* ---- gates ----------------------------------------------------------------------- */
-/* n_buf: 1 = one tile buffer per CTA (more resident CTAs), 2 = the next tile is prefetched
- * while the current one is worked on */
-template <typename real>
-cudaError_t launch_tile_pass(const PassProgram<real> &prog, void *amp, int n_buf, cudaStream_t stream);
-/* smem bytes the tile kernel needs for (T, L), n_stages stages and n_buf tile buffers */
-size_t tile_pass_smem_bytes(int prec, int T, int L, int n_stages, int n_buf);
-cudaError_t tile_pass_configure(int max_smem_optin, int sm_count);
-
-/* the same pass with TMA tensor-map staging (kernels_tma.cu); needs prog.n_groups >= 1;
+/* the fused gate pass, TMA tensor-map staging (kernels_tma.cu); needs prog.n_groups >= 1;
  * n_buf = 2 or 3 tile buffers per CTA; min_ctas = resident CTAs per SM the register budget is
  * set for (3: 80 registers per thread, 2: up to 128) */
 template <typename real>
@@ -50,10 +44,14 @@ cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf,
 size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops);
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);
 void tma_pass_set_warp_specialised(int on); /* 1: a producer warp owns the TMA traffic (default 0) */
+void tma_pass_set_l2_hint(int mode);    /* 1: loads, 2: stores, 3: both with an L2 evict_first policy */
+void tma_pass_set_debug_mode(int mode); /* measurement only: 1 = stages without ops, 2 = no stages     */
 void tma_pass_phase_report(); /* no-op unless built with -DQGB_PHASE_TIMING */
 
+/* one gate per launch: pairs whose ctrl_mask bits are 1 and zero_mask bits are 0.  exact: the
+ * reference CPU runtime's arithmetic, operation by operation (bit-identical amplitudes) */
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
-                               uint64_t ctrl_mask, uint64_t zero_mask, cudaStream_t stream);
+                               uint64_t ctrl_mask, uint64_t zero_mask, bool exact, cudaStream_t stream);
 
 /* ---- state-vector maintenance ------------------------------------------------------ */
 cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,
@@ -90,10 +88,17 @@ cudaError_t launch_get_states(int prec, void *d_out, int mathop, const GatherPar
 /* marginal probabilities: d_out[d] (double), d in [first, first+count):
  * sum_{h < 2^n_hidden} prod_qs |amp_qs[perm((d << n_hidden) | h)]|^2 (product in `real`, sum in double) */
 cudaError_t launch_prob_array(int prec, double *d_out, const GatherParams &gp, int n_hidden,
-                              int64_t first, int64_t count, cudaStream_t stream);
-/* d_out[j] = sum of 2^log2_group consecutive d_in values (sequential, double), j < count */
+                              int64_t first, int64_t count, bool compat, cudaStream_t stream);
+/* d_out[j] = sum of 2^log2_group consecutive d_in values (sequential; in double, or in float when
+ * fp32_sums), j < count */
 cudaError_t launch_reduce_groups(double *d_out, const double *d_in, int log2_group, int64_t count,
-                                 cudaStream_t stream);
+                                 bool fp32_sums, cudaStream_t stream);
+/* reference-compatible pool scan (CPUSamplingPool.cpp:13-47): sequential running sums in the state
+ * precision over n_spans spans of `span` entries; then (p + offset of the span) * norm */
+cudaError_t launch_compat_scan(int prec, double *d_prob, int64_t n, int64_t span, int n_spans,
+                               double *d_span_total, cudaStream_t stream);
+cudaError_t launch_compat_apply(int prec, double *d_prob, int64_t n, int64_t span, const double *d_span_offset,
+                                double norm, cudaStream_t stream);
 /* double -> real conversion of a device array (for handing the prob array to the host) */
 cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, int64_t count,
                                     cudaStream_t stream);

@@ -65,6 +65,45 @@ __device__ __forceinline__ double block_sum(double v) {
     return v;
 }
 
+/* ---- one (multi-)controlled 2x2 per launch, one amplitude pair per thread ------------------
+ * The path of state vectors too small for the fused pass (dynamic qubit grouping creates many)
+ * and of the options fuse = 0 / exact = 1.  EXACT: the arithmetic of CPUQubitProcessor.cpp:316-324
+ * operation by operation — std::complex products (ac - bd, ad + bc) rounded term by term, then the
+ * complex sum, nothing contracted into FMAs — so the amplitudes are bit-identical to the
+ * reference CPU runtime's. */
+template <typename real> struct Mat2 { real m[8]; };
+
+template <typename real, bool EXACT>
+__global__ void __launch_bounds__(256)
+simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs, const SortedBits skip,
+                   uint64_t target_bit, uint64_t ctrl_mask, const Mat2<real> mat) {
+    typedef typename Cplx<real>::type cplx;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_pairs) return;
+    uint64_t idx = gid; /* a 0 at every skipped position (target, controls, zero-controls), ascending */
+    for (int i = 0; i < skip.n; ++i) idx = insert_zero(idx, skip.pos[i]);
+    const uint64_t i0 = idx | ctrl_mask, i1 = i0 | target_bit;
+    const cplx q0 = amp[i0], q1 = amp[i1];
+    const real *m = mat.m;
+    cplx o0, o1;
+    if (EXACT) {
+        cplx m00, m01, m10, m11;
+        m00.x = m[0], m00.y = m[1], m01.x = m[2], m01.y = m[3];
+        m10.x = m[4], m10.y = m[5], m11.x = m[6], m11.y = m[7];
+        const cplx a0 = cmul_exact(m00, q0), b0 = cmul_exact(m01, q1);
+        const cplx a1 = cmul_exact(m10, q0), b1 = cmul_exact(m11, q1);
+        o0.x = add_rn(a0.x, b0.x), o0.y = add_rn(a0.y, b0.y);
+        o1.x = add_rn(a1.x, b1.x), o1.y = add_rn(a1.y, b1.y);
+    } else {
+        o0.x = m[0] * q0.x - m[1] * q0.y + m[2] * q1.x - m[3] * q1.y;
+        o0.y = m[0] * q0.y + m[1] * q0.x + m[2] * q1.y + m[3] * q1.x;
+        o1.x = m[4] * q0.x - m[5] * q0.y + m[6] * q1.x - m[7] * q1.y;
+        o1.y = m[4] * q0.y + m[5] * q0.x + m[6] * q1.y + m[7] * q1.x;
+    }
+    amp[i0] = o0;
+    amp[i1] = o1;
+}
+
 /* ---- reset to a basis state (CPUQubitProcessor.cpp:61-73) ----------------------------- */
 template <typename real>
 __global__ void set_one_kernel(typename Cplx<real>::type *amp, uint64_t one_at) {
@@ -226,7 +265,10 @@ get_states_kernel(void *__restrict__ out, const __grid_constant__ GatherParams g
 }
 
 /* ---- marginal probabilities, hidden lanes in the LSBs (CPUQubitsStatesGetter.cpp:159-254) -- */
-template <typename real>
+/* ACC = double: the engine's default (hidden lanes summed in double).  ACC = real: the reference
+ * CPU runtime's own accumulation, value for value (CPUQubitsStatesGetter.cpp:186-201: a running
+ * sum in `real`, started at 0, over 2^n_hidden consecutive indices) — option pool_compat_workers. */
+template <typename real, typename ACC>
 __global__ void __launch_bounds__(256)
 prob_array_kernel(double *__restrict__ out, const __grid_constant__ GatherParams gp, int n_hidden,
                   int64_t first, int64_t count) {
@@ -235,7 +277,7 @@ prob_array_kernel(double *__restrict__ out, const __grid_constant__ GatherParams
     const uint64_t n_sum = 1ull << n_hidden;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
         const uint64_t d = (uint64_t)(first + j);
-        double sum = 0.;
+        ACC sum = (ACC)0;
         for (uint64_t h = 0; h < n_sum; ++h) {
             const uint64_t ext = (d << n_hidden) | h;
             real v = (real)1;
@@ -243,21 +285,74 @@ prob_array_kernel(double *__restrict__ out, const __grid_constant__ GatherParams
                 const cplx s = reinterpret_cast<const cplx *>(gp.qs[q].amp)[ext_to_local(gp.qs[q], ext)];
                 v = mul_rn(v, abs2_exact(s));
             }
-            sum = add_rn(sum, (double)v);
+            sum = add_rn(sum, (ACC)v);
         }
-        out[j] = sum;
+        out[j] = (double)sum;
     }
 }
 
-/* out[j] = sum of 2^log2_group consecutive inputs (sequential, double) */
+/* out[j] = sum of 2^log2_group consecutive inputs (sequential, in ACC: double, or the state
+ * precision of the reference's second and later reduction levels, CPUQubitsStatesGetter.cpp:224-231) */
+template <typename ACC>
 __global__ void __launch_bounds__(256)
 reduce_groups_kernel(double *__restrict__ out, const double *__restrict__ in, int log2_group, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t g = 1ll << log2_group;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
-        double sum = 0.;
-        for (int64_t h = 0; h < g; ++h) sum = add_rn(sum, in[j * g + h]);
-        out[j] = sum;
+        ACC sum = (ACC)0;
+        for (int64_t h = 0; h < g; ++h) sum = add_rn(sum, (ACC)in[j * g + h]);
+        out[j] = (double)sum;
+    }
+}
+
+/* ---- sampling pool, reference-compatible scan (CPUSamplingPool.cpp:13-47) -------------------
+ * The reference scans sequentially, in the state precision V, one span per worker thread
+ * (Parallel.h:12-23: spans of ceil(N / W) rounded up to 16), prefix-sums the W span totals in V,
+ * then adds the offset of the span and multiplies by V(1) / total.  A floating-point running sum
+ * cannot be re-associated without changing its roundings, so this mode keeps the order: ONE warp
+ * per span, the lanes move 32 x 16 values at a time between HBM and shared memory (coalesced),
+ * lane 0 runs the sum.  Values are kept as doubles that hold V values exactly.  Used only with
+ * option pool_compat_workers = W (index-exact parity with a W-worker reference); the default
+ * pool is the parallel float64 scan below. */
+#define COMPAT_CHUNK 2048
+template <typename V>
+__global__ void __launch_bounds__(32)
+compat_scan_kernel(double *__restrict__ prob, int64_t n, int64_t span, double *__restrict__ span_total) {
+    __shared__ double buf[COMPAT_CHUNK];
+    const int64_t begin = span * blockIdx.x < n ? span * blockIdx.x : n;
+    const int64_t end = begin + span < n ? begin + span : n;
+    const int lane = threadIdx.x;
+    V v = (V)0;
+    for (int64_t base = begin; base < end; base += COMPAT_CHUNK) {
+        const int64_t left = end - base;
+        const int len = left < COMPAT_CHUNK ? (int)left : COMPAT_CHUNK;
+        for (int i = lane; i < len; i += 32) buf[i] = prob[base + i];
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll 8
+            for (int i = 0; i < len; ++i) {
+                v = add_rn(v, (V)buf[i]);
+                buf[i] = (double)v;
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < len; i += 32) prob[base + i] = buf[i];
+        __syncwarp();
+    }
+    if (lane == 0) span_total[blockIdx.x] = (double)v;
+}
+
+/* prob[idx] = (prob[idx] + offset of its span) * norm, in V; span 0 is only multiplied */
+template <typename V>
+__global__ void __launch_bounds__(256)
+compat_apply_kernel(double *__restrict__ prob, int64_t n, int64_t span, const double *__restrict__ span_offset,
+                    double norm) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t t = i / span;
+        V p = (V)prob[i];
+        if (t > 0) p = add_rn(p, (V)span_offset[t - 1]);
+        prob[i] = (double)mul_rn(p, (V)norm);
     }
 }
 
@@ -387,6 +482,38 @@ const unsigned kStreamCap = 148 * 16;
 
 } // namespace
 
+cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
+                               uint64_t ctrl_mask, uint64_t zero_mask, bool exact, cudaStream_t stream) {
+    SortedBits skip;
+    skip.n = 0;
+    const uint64_t touched = ctrl_mask | zero_mask | (1ull << target);
+    for (int lane = 0; lane < n_lanes; ++lane)
+        if (touched & (1ull << lane)) skip.pos[skip.n++] = (int8_t)lane;
+    const uint64_t n_pairs = 1ull << (n_lanes - skip.n);
+    const unsigned nthr = 256;
+    const unsigned nblocks = (unsigned)((n_pairs + nthr - 1) / nthr);
+    if (prec == 1) {
+        Mat2<double> m;
+        for (int i = 0; i < 8; ++i) m.m[i] = mat8[i];
+        if (exact)
+            simple_gate_kernel<double, true><<<nblocks, nthr, 0, stream>>>(reinterpret_cast<double2 *>(amp), n_pairs, skip,
+                                                                          1ull << target, ctrl_mask, m);
+        else
+            simple_gate_kernel<double, false><<<nblocks, nthr, 0, stream>>>(reinterpret_cast<double2 *>(amp), n_pairs, skip,
+                                                                           1ull << target, ctrl_mask, m);
+    } else {
+        Mat2<float> m;
+        for (int i = 0; i < 8; ++i) m.m[i] = (float)mat8[i];
+        if (exact)
+            simple_gate_kernel<float, true><<<nblocks, nthr, 0, stream>>>(reinterpret_cast<float2 *>(amp), n_pairs, skip,
+                                                                         1ull << target, ctrl_mask, m);
+        else
+            simple_gate_kernel<float, false><<<nblocks, nthr, 0, stream>>>(reinterpret_cast<float2 *>(amp), n_pairs, skip,
+                                                                          1ull << target, ctrl_mask, m);
+    }
+    return cudaGetLastError();
+}
+
 cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,
                                    cudaStream_t stream) {
     const size_t bytes = n_amps * (prec == 1 ? 16 : 8);
@@ -508,19 +635,43 @@ cudaError_t launch_get_states(int prec, void *d_out, int mathop, const GatherPar
 }
 
 cudaError_t launch_prob_array(int prec, double *d_out, const GatherParams &gp, int n_hidden, int64_t first,
-                              int64_t count, cudaStream_t stream) {
+                              int64_t count, bool compat, cudaStream_t stream) {
     const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
-    if (prec == 1)
-        prob_array_kernel<double><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
+    if (prec == 1) /* complex128: `real` is double, the two accumulations coincide */
+        prob_array_kernel<double, double><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
+    else if (compat)
+        prob_array_kernel<float, float><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
     else
-        prob_array_kernel<float><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
+        prob_array_kernel<float, double><<<nblocks, 256, 0, stream>>>(d_out, gp, n_hidden, first, count);
     return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_groups(double *d_out, const double *d_in, int log2_group, int64_t count,
-                                 cudaStream_t stream) {
+                                 bool fp32_sums, cudaStream_t stream) {
     const unsigned nblocks = grid_for((uint64_t)count, 256, kStreamCap);
-    reduce_groups_kernel<<<nblocks, 256, 0, stream>>>(d_out, d_in, log2_group, count);
+    if (fp32_sums)
+        reduce_groups_kernel<float><<<nblocks, 256, 0, stream>>>(d_out, d_in, log2_group, count);
+    else
+        reduce_groups_kernel<double><<<nblocks, 256, 0, stream>>>(d_out, d_in, log2_group, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compat_scan(int prec, double *d_prob, int64_t n, int64_t span, int n_spans,
+                               double *d_span_total, cudaStream_t stream) {
+    if (prec == 1)
+        compat_scan_kernel<double><<<(unsigned)n_spans, 32, 0, stream>>>(d_prob, n, span, d_span_total);
+    else
+        compat_scan_kernel<float><<<(unsigned)n_spans, 32, 0, stream>>>(d_prob, n, span, d_span_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compat_apply(int prec, double *d_prob, int64_t n, int64_t span, const double *d_span_offset,
+                                double norm, cudaStream_t stream) {
+    const unsigned nblocks = grid_for((uint64_t)n, 256, kStreamCap);
+    if (prec == 1)
+        compat_apply_kernel<double><<<nblocks, 256, 0, stream>>>(d_prob, n, span, d_span_offset, norm);
+    else
+        compat_apply_kernel<float><<<nblocks, 256, 0, stream>>>(d_prob, n, span, d_span_offset, norm);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,10 @@ struct TmaGeometry {
     int32_t base_shift[QGB_MAX_GROUPS]; /* lane of the group's first non-tile lane            */
     unsigned long long *phase;       /* QGB_PHASE_TIMING=1: cycles per phase, summed over warp 0 of */
                                      /* every CTA (diagnostic build only, see tma_pass_phase_report) */
+    int32_t l2_hint;                 /* 1: loads, 2: stores, 3: both carry an L2 evict_first policy  */
+    int32_t debug_mode;              /* measurement only (option debug_pass_mode): 1 = the stages   */
+                                     /* load and store their registers but skip the ops, 2 = no     */
+                                     /* stages at all (the tile only travels in and out)             */
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +86,25 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap *map, const void 
                                              int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];\n" ::"l"(map),
                  "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_5d_hint(void *dst, const CUtensorMap *map, uint64_t *bar, int c1, int c2,
+                                                 int c3, int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;\n" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_5d_hint(const CUtensorMap *map, const void *src, int c1, int c2, int c3,
+                                                  int c4, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4, %5}], [%6], %7;\n" ::"l"(map),
+                 "r"(0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(src)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
@@ -269,14 +292,118 @@ __device__ __forceinline__ void lean_swap(typename Cplx<real>::type (&a)[1 << K]
 
 #define QGB_J(j) ((j) < K ? (j) : 0)
 
+/* ---- OP_SHEAR: M = phi P^s N, N = [[1,x],[0,1]] [[1,0],[g,1]] [[1,y],[0,1]] (program.h) -----------
+ * q0 += y q1;  q1 += g q0;  q0 += x q1 — twelve FMAs per pair, every one of them in place (no
+ * temporaries, no register moves at the end of the op body), against sixteen plus ~30 moves for
+ * the direct 2x2.  Coefficient block: y, g, x as (re, im), then two unused reals. */
+template <typename real> struct Sh6;
+template <> struct Sh6<double> {
+    double yr, yi, gr, gi, xr, xi;
+    __device__ __forceinline__ void load(const double *p) {
+        const double2 *q = reinterpret_cast<const double2 *>(p);
+        const double2 t0 = q[0], t1 = q[1], t2 = q[2];
+        yr = t0.x, yi = t0.y, gr = t1.x, gi = t1.y, xr = t2.x, xi = t2.y;
+    }
+};
+template <> struct Sh6<float> {
+    u64 yr, yn, gr, gn, xr, xn; /* (re, re) and (-im, im) of y, g, x */
+    __device__ __forceinline__ void load(const float *p) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+        const float4 t0 = q[0], t1 = q[1], t2 = q[2]; /* MatLayout<float>: 4 real parts, then (-im, im) x 4 */
+        yr = pk2(t0.x, t0.x), gr = pk2(t0.y, t0.y), xr = pk2(t0.z, t0.z);
+        yn = pk2(t1.x, t1.y), gn = pk2(t1.z, t1.w), xn = pk2(t2.x, t2.y);
+    }
+};
+
+__device__ __forceinline__ void pair_shear(double2 &q0, double2 &q1, const Sh6<double> &c) {
+    q0.x = fma(c.yr, q1.x, q0.x);
+    q0.y = fma(c.yr, q1.y, q0.y);
+    q0.x = fma(-c.yi, q1.y, q0.x);
+    q0.y = fma(c.yi, q1.x, q0.y);
+    q1.x = fma(c.gr, q0.x, q1.x);
+    q1.y = fma(c.gr, q0.y, q1.y);
+    q1.x = fma(-c.gi, q0.y, q1.x);
+    q1.y = fma(c.gi, q0.x, q1.y);
+    q0.x = fma(c.xr, q1.x, q0.x);
+    q0.y = fma(c.xr, q1.y, q0.y);
+    q0.x = fma(-c.xi, q1.y, q0.x);
+    q0.y = fma(c.xi, q1.x, q0.y);
+}
+__device__ __forceinline__ void pair_shear(float2 &x0, float2 &x1, const Sh6<float> &c) {
+    u64 q0 = as_u64(x0), q1 = as_u64(x1);
+    q0 = fma2(c.yr, q1, q0);
+    q0 = fma2(c.yn, swap2(q1), q0);
+    q1 = fma2(c.gr, q0, q1);
+    q1 = fma2(c.gn, swap2(q0), q1);
+    q0 = fma2(c.xr, q1, q0);
+    q0 = fma2(c.xn, swap2(q1), q0);
+    x0 = as_f2(q0);
+    x1 = as_f2(q1);
+}
+
+/* MODE as lean_gen */
+template <typename real, int K, int J, int MODE, int J2>
+__device__ __forceinline__ void lean_shear(typename Cplx<real>::type (&a)[1 << K], const Sh6<real> &c, uint32_t regmask) {
+#pragma unroll
+    for (int r0 = 0; r0 < (1 << K); ++r0) {
+        if (r0 & (1 << J)) continue;
+        if (MODE == 2 && (r0 & (1 << J2))) continue;
+        if (MODE == 3 && !(r0 & (1 << J2))) continue;
+        if (MODE == 1 && !(regmask & (1u << r0))) continue;
+        pair_shear(a[r0], a[r0 | (1 << J)], c);
+    }
+}
+
+template <typename real, int K, int J, int J2>
+__device__ __forceinline__ void lean_shear_regmux(typename Cplx<real>::type (&a)[1 << K], const Sh6<real> &c0,
+                                                  const real *mats) {
+    if (J == J2) return; /* never planned */
+    Sh6<real> c1;
+    c1.load(mats + MatLayout<real>::kStride); /* in flight under the first half */
+    lean_shear<real, K, J, 2, (J == J2 ? 0 : J2)>(a, c0, 0u);
+    lean_shear<real, K, J, 3, (J == J2 ? 0 : J2)>(a, c1, 0u);
+}
+
+/* the sheared ops of a pass (kept apart from lean_apply_op: their coefficient block is shorter) */
+template <typename real, int K>
+__device__ __forceinline__ void lean_apply_shear(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
+                                                 const real *mo, const real *mm) {
+    Sh6<real> c;
+    c.load(mm);
+    switch (op.code) {
+    case OPC_SHEAR(0): lean_shear<real, K, 0, 0, 0>(a, c, 0u); break;
+    case OPC_SHEAR(1): lean_shear<real, K, QGB_J(1), 0, 0>(a, c, 0u); break;
+    case OPC_SHEAR(2): lean_shear<real, K, QGB_J(2), 0, 0>(a, c, 0u); break;
+    case OPC_SHEAR(3): if (K > 3) lean_shear<real, K, QGB_J(3), 0, 0>(a, c, 0u); break;
+    case OPC_SHEAR_MASKED(0): lean_shear<real, K, 0, 1, 0>(a, c, op.regmask); break;
+    case OPC_SHEAR_MASKED(1): lean_shear<real, K, QGB_J(1), 1, 0>(a, c, op.regmask); break;
+    case OPC_SHEAR_MASKED(2): lean_shear<real, K, QGB_J(2), 1, 0>(a, c, op.regmask); break;
+    case OPC_SHEAR_MASKED(3): if (K > 3) lean_shear<real, K, QGB_J(3), 1, 0>(a, c, op.regmask); break;
+    case OPC_SHEAR_REGMUX(0, 1): lean_shear_regmux<real, K, 0, QGB_J(1)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(0, 2): lean_shear_regmux<real, K, 0, QGB_J(2)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(0, 3): if (K > 3) lean_shear_regmux<real, K, 0, QGB_J(3)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(1, 0): lean_shear_regmux<real, K, QGB_J(1), 0>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(1, 2): lean_shear_regmux<real, K, QGB_J(1), QGB_J(2)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(1, 3): if (K > 3) lean_shear_regmux<real, K, QGB_J(1), QGB_J(3)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(2, 0): lean_shear_regmux<real, K, QGB_J(2), 0>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(2, 1): lean_shear_regmux<real, K, QGB_J(2), QGB_J(1)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(2, 3): if (K > 3) lean_shear_regmux<real, K, QGB_J(2), QGB_J(3)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(3, 0): if (K > 3) lean_shear_regmux<real, K, QGB_J(3), 0>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(3, 1): if (K > 3) lean_shear_regmux<real, K, QGB_J(3), QGB_J(1)>(a, c, mo); break;
+    case OPC_SHEAR_REGMUX(3, 2): if (K > 3) lean_shear_regmux<real, K, QGB_J(3), QGB_J(2)>(a, c, mo); break;
+    default: break;
+    }
+}
+
 /* One op on the registers of a thread that takes part in it (`mm` = the op's matrix or factor
  * already selected for this thread and tile, `mo` = the op's [m | m1] block).  The matrix is
  * fetched BEFORE the dispatch so the shared-memory latency hides under the switch. */
-template <typename real, int K>
+template <typename real, int K, bool DIRECT>
 __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 << K], const Op<real> &op,
                                               const real *mo, const real *mm) {
     Mat8<real> m;
     m.load(mm);
+    if (DIRECT) { /* direct 2x2 bodies: compiled into the variant that serves passes with OP_GEN ops */
     switch (op.code) {
     case OPC_GEN(0): lean_gen<real, K, 0, 0, 0>(a, m, 0u); break;
     case OPC_GEN(1): lean_gen<real, K, QGB_J(1), 0, 0>(a, m, 0u); break;
@@ -298,6 +425,10 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
     case OPC_GEN_REGMUX(3, 0): if (K > 3) lean_regmux<real, K, QGB_J(3), 0>(a, m, mo); break;
     case OPC_GEN_REGMUX(3, 1): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(1)>(a, m, mo); break;
     case OPC_GEN_REGMUX(3, 2): if (K > 3) lean_regmux<real, K, QGB_J(3), QGB_J(2)>(a, m, mo); break;
+    default: break;
+    }
+    }
+    switch (op.code) {
     case OPC_SWAP(0): lean_swap<real, K, 0>(a, op.regmask); break;
     case OPC_SWAP(1): lean_swap<real, K, QGB_J(1)>(a, op.regmask); break;
     case OPC_SWAP(2): lean_swap<real, K, QGB_J(2)>(a, op.regmask); break;
@@ -331,7 +462,7 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
  * timing build).  Consumers synchronise among themselves on a named barrier.  Measured 5-7%
  * SLOWER than the unspecialised kernel (the other resident CTAs already cover that wait, the
  * extra warp costs registers): kept as an option, off by default. */
-template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT>
 __global__ void __launch_bounds__(NT, MINB)
 tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_constant__ CUtensorMap tmap,
                 const __grid_constant__ TmaGeometry geo) {
@@ -399,14 +530,20 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         for (int d = 0; d < QGB_MAX_GROUPS; ++d)
             c[d] = (int)((((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.tbits[d]);
         mbar_expect_tx(&full[b], tile_bytes);
-        tma_load_5d(tiles + (size_t)b * tile_bytes, &tmap, &full[b], c[0], c[1], c[2], c[3]);
+        if (geo.l2_hint & 1)
+            tma_load_5d_hint(tiles + (size_t)b * tile_bytes, &tmap, &full[b], c[0], c[1], c[2], c[3], l2_evict_first_policy());
+        else
+            tma_load_5d(tiles + (size_t)b * tile_bytes, &tmap, &full[b], c[0], c[1], c[2], c[3]);
     };
     auto issue_store = [&](uint64_t t, int b) {
         int c[QGB_MAX_GROUPS];
 #pragma unroll
         for (int d = 0; d < QGB_MAX_GROUPS; ++d)
             c[d] = (int)((((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.tbits[d]);
-        tma_store_5d(&tmap, tiles + (size_t)b * tile_bytes, c[0], c[1], c[2], c[3]);
+        if (geo.l2_hint & 2)
+            tma_store_5d_hint(&tmap, tiles + (size_t)b * tile_bytes, c[0], c[1], c[2], c[3], l2_evict_first_policy());
+        else
+            tma_store_5d(&tmap, tiles + (size_t)b * tile_bytes, c[0], c[1], c[2], c[3]);
         bulk_commit();
     };
 
@@ -480,38 +617,42 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         PH_MARK(ph_wait);
         unsigned char *buf = tiles + (size_t)b * tile_bytes;
 
-        for (int s = 0; s < prog.n_stages; ++s) {
+        for (int s = 0; s < prog.n_stages && geo.debug_mode < 2; ++s) {
             const Stage &st = prog.stage[s];
             if (st.op_begin == st.op_end) continue;
             const uint32_t packed = lut[s * nthr + tid];
             const uint32_t sbyte = (packed >> 16) << 3;
 
-            /* slot of register r: base slot ^ XOR of the per-bit constants over the bits of r */
-            uint32_t off[1 << K];
-            off[0] = sbyte;
-#pragma unroll
-            for (int r = 1; r < (1 << K); ++r) {
-                const int low = r & -r; /* lowest set bit */
-                const int j = low == 1 ? 0 : (low == 2 ? 1 : (low == 4 ? 2 : 3));
-                off[r] = off[r ^ low] ^ st.xb[j];
-            }
+            /* slot of register r: base slot ^ XOR of the per-bit constants over the bits of r.  The
+             * constants are CTA-uniform, the slots are recomputed at the store (a table of 2^K
+             * slots kept across the ops costs 2^K registers and spilled) */
+            const uint32_t x0 = st.xb[0], x1 = st.xb[1], x2 = st.xb[2], x3 = K > 3 ? st.xb[3] : 0u;
+#define QGB_SLOT(base, r) ((base) ^ (((r) & 1) ? x0 : 0u) ^ (((r) & 2) ? x1 : 0u) ^ (((r) & 4) ? x2 : 0u) ^ (((r) & 8) ? x3 : 0u))
             cplx a[1 << K];
 #pragma unroll
-            for (int r = 0; r < (1 << K); ++r) a[r] = *reinterpret_cast<const cplx *>(buf + off[r]);
+            for (int r = 0; r < (1 << K); ++r) a[r] = *reinterpret_cast<const cplx *>(buf + QGB_SLOT(sbyte, r));
             PH_MARK(ph_load);
 
-            {
+            if (geo.debug_mode == 0) {
                 uint32_t bit = 1u << st.op_begin;
                 const real *mo = mats + 2 * MS * st.op_begin;
                 for (int o = st.op_begin; o < st.op_end; ++o, bit <<= 1, mo += 2 * MS) {
                     if (!(eff & bit)) continue;
-                    lean_apply_op<real, K>(a, prog.op[o], mo, mo + ((sel & bit) ? MS : 0));
+                    const Op<real> &op = prog.op[o];
+                    const real *mm = mo + ((sel & bit) ? MS : 0);
+                    if (op.code >= OPC_SHEAR(0))
+                        lean_apply_shear<real, K>(a, op, mo, mm);
+                    else
+                        lean_apply_op<real, K, DIRECT>(a, op, mo, mm);
                 }
             }
 
             PH_MARK(ph_ops);
+            /* registers relabelled by the stage's shears go to the slots they now stand for */
+            const uint32_t sstore = sbyte ^ st.store_xor;
 #pragma unroll
-            for (int r = 0; r < (1 << K); ++r) *reinterpret_cast<cplx *>(buf + off[r]) = a[r];
+            for (int r = 0; r < (1 << K); ++r) *reinterpret_cast<cplx *>(buf + QGB_SLOT(sstore, r)) = a[r];
+#undef QGB_SLOT
             if (s + 1 < prog.n_stages) {
                 if (st.warp_local)
                     __syncwarp(); /* the next stage reads only what this warp wrote (planner.cpp) */
@@ -557,6 +698,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 EncodeTiledFn g_encode = nullptr;
 unsigned long long *g_phase = nullptr;
 int g_tma_ws = 0; /* measured 5-7% slower than the unspecialised kernel on B200 (profiles/r1z): off */
+int g_tma_l2_hint = 0;
+int g_tma_debug_mode = 0;
 int g_tma_sm_count = 148;
 int g_tma_max_smem = 48 * 1024;
 
@@ -584,6 +727,8 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     int consumed = 0;
     geo->n_groups = prog.n_groups;
     geo->phase = g_phase;
+    geo->l2_hint = g_tma_l2_hint;
+    geo->debug_mode = g_tma_debug_mode;
     for (int d = 0; d < QGB_MAX_GROUPS; ++d) {
         if (d < prog.n_groups) {
             const int s = prog.grp_start[d], t = prog.grp_t[d], r = prog.grp_r[d];
@@ -614,11 +759,11 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
-cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
-                               size_t smem, cudaStream_t stream) {
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT>
+cudaError_t launch_tma_variant2(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
+                                size_t smem, cudaStream_t stream) {
     static int configured = 0;
-    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF, WS>;
+    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF, WS, DIRECT>;
     if (!configured) {
         cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_max_smem);
         if (rc != cudaSuccess) return rc;
@@ -634,6 +779,14 @@ cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap 
     const unsigned nblocks = (unsigned)(n_tiles < resident ? n_tiles : resident);
     kernel<<<nblocks, nthr, smem, stream>>>(prog, map, geo);
     return cudaGetLastError();
+}
+
+/* passes without direct 2x2 ops (every dense gate sheared) run the variant compiled without those bodies */
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
+cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
+                               size_t smem, cudaStream_t stream) {
+    if (prog.n_direct == 0) return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, false>(prog, map, geo, smem, stream);
+    return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, true>(prog, map, geo, smem, stream);
 }
 
 template <typename real, int K>
@@ -682,6 +835,8 @@ size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int 
 }
 
 void tma_pass_set_warp_specialised(int on) { g_tma_ws = on ? 1 : 0; }
+void tma_pass_set_l2_hint(int mode) { g_tma_l2_hint = mode & 3; }
+void tma_pass_set_debug_mode(int mode) { g_tma_debug_mode = mode; }
 
 /* Diagnostic (compile with -DQGB_PHASE_TIMING): where warp 0 of every CTA spends its cycles. */
 void tma_pass_phase_report() {

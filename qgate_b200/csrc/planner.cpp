@@ -10,6 +10,8 @@
 #include "planner.h"
 
 #include <algorithm>
+#include <cmath>
+#include <complex>
 #include <cstring>
 
 namespace qgb {
@@ -97,6 +99,38 @@ inline bool acts_nondiag_on(const Gate &p, int lane) { return p.target == lane &
 
 const double kIdentity[8] = {1., 0., 0., 0., 0., 0., 1., 0.};
 
+typedef std::complex<double> cd;
+
+/* M (row-major (re, im) x 4) = phi * P^s * N with det N = 1 and
+ * N = [[1,x],[0,1]] [[1,0],[g,1]] [[1,y],[0,1]]: g = N10, x = (N00 - 1) / g, y = (N11 - 1) / g.
+ * P exchanges the two outputs (rows).  Of the two square roots of the determinant the one with
+ * Re(N00 + N11) >= 0 is taken (smaller x, y).  `size` = the largest coefficient magnitude: the
+ * error growth of the three shears.  False when M is singular or g vanishes. */
+struct ShearCoef {
+    double y[2], g[2], x[2], phi[2];
+    double size;
+};
+
+bool shear_factor(const double *m, int s, ShearCoef &out) {
+    cd a(m[0], m[1]), b(m[2], m[3]), c(m[4], m[5]), d(m[6], m[7]);
+    if (s) std::swap(a, c), std::swap(b, d);
+    const cd det = a * d - b * c;
+    const double ad = std::abs(det);
+    if (!(ad > 1e-280) || !std::isfinite(ad)) return false;
+    cd phi = std::sqrt(det);
+    if (((a + d) / phi).real() < 0.) phi = -phi;
+    const cd n00 = a / phi, n11 = d / phi, g = c / phi;
+    const double ag = std::abs(g);
+    if (!(ag > 1e-280)) return false;
+    const cd x = (n00 - 1.) / g, y = (n11 - 1.) / g;
+    out.y[0] = y.real(), out.y[1] = y.imag();
+    out.g[0] = g.real(), out.g[1] = g.imag();
+    out.x[0] = x.real(), out.x[1] = x.imag();
+    out.phi[0] = phi.real(), out.phi[1] = phi.imag();
+    out.size = std::max(std::abs(x), std::max(std::abs(y), ag));
+    return std::isfinite(out.size);
+}
+
 } // namespace
 
 /* Host-side merging (matrices composed in double).  The new gate g is moved BACKWARDS over the
@@ -180,7 +214,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
     std::vector<uint64_t> stageR; /* lane masks of the register bits of each stage */
     std::vector<uint64_t> stageMux; /* multiplexer lanes of the gates of each stage */
     int first_block = -1;
-    int cost = 0;
+    int cost = 0, slots = 0;
 
     for (int i = 0; i < (int)queue.size(); ++i) {
         if (first_block >= 0 && i - first_block > cfg.lookahead) break;
@@ -190,8 +224,11 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         const uint64_t xq = diag ? 0 : tm;
         const uint64_t zq = g.ctrl_mask | (diag ? tm : 0) | (g.mux >= 0 ? (1ull << g.mux) : 0ull);
         bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
-        const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : 4);
-        if (!blocked && ((int)picked.size() >= max_ops || (cost + gcost > cfg.max_cost && !picked.empty())))
+        const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4));
+        /* op slots: a sheared gate with controls or a multiplexer may need its phase applied as one
+         * more (diagonal) op of this pass */
+        const int gslots = (cfg.shear && !diag && (g.mux >= 0 || g.ctrl_mask != 0)) ? 2 : 1;
+        if (!blocked && !picked.empty() && (slots + gslots > max_ops || cost + gcost > cfg.max_cost))
             blocked = true;
         bool add_lane = false;
         if (!blocked && xq && !(S & xq)) {
@@ -230,6 +267,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         if (g.mux >= 0) stageMux.back() |= 1ull << g.mux;
         picked.push_back({i, (int)stageR.size() - 1});
         cost += gcost;
+        slots += gslots;
     }
 
     /* fill the tile with the highest unused lanes when fewer than T were needed (keeps the
@@ -328,18 +366,40 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         }
     }
 
-    /* ops, grouped by stage in pick order (pick order is stage-monotone) */
+    /* ops, grouped by stage in pick order (pick order is stage-monotone).
+     *
+     * Dense gates become OP_SHEAR where the factorisation M = phi * P^s * N is well conditioned
+     * (shear_factor).  What it leaves behind:
+     *   P^s   a relabelling of the stage's registers (`flip`): every later op of the stage is
+     *         expressed in relabelled registers here, the kernel stores through Stage::store_xor;
+     *   phi   a diagonal "residual" (a scalar, or diag(phi0, phi1) on the multiplexer lane, or a
+     *         controlled phase) that commutes with the gate itself: it is folded into the next
+     *         gate that acts non-diagonally on its lane (picked later in this pass, or still
+     *         queued), or applied as a diagonal op when there is none. */
+    std::vector<char> is_picked(queue.size(), 0);
+    for (const Picked &pk : picked) is_picked[pk.queue_idx] = 1;
+    std::vector<Gate> deferred; /* residuals for the front of the remaining queue */
+    const int op_limit = max_ops;
     int n_ops = 0;
     int cur_stage = -1;
-    for (const Picked &pk : picked) {
-        const Gate &g = queue[pk.queue_idx];
-        while (cur_stage < pk.stage) {
-            if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;
-            ++cur_stage;
-            prog.stage[cur_stage].op_begin = (int16_t)n_ops;
-        }
+    uint32_t flip = 0; /* register relabelling of the open stage */
+    stats.shear_ops = stats.direct_ops = stats.residual_ops = 0;
+    prog.n_direct = 0;
+
+    auto close_stage = [&](int sidx) {
+        Stage &st = prog.stage[sidx];
+        st.op_end = (int16_t)n_ops;
+        st.store_flip = flip;
+        st.store_xor = 0;
+        for (int j = 0; j < K; ++j)
+            if (flip & (1u << j)) st.store_xor ^= st.xb[j];
+    };
+
+    /* one op for gate g in stage sidx; dense gates may leave a residual in `res` (res_kind: 0 none,
+     * 1 diagonal gate `res`) */
+    auto lower = [&](const Gate &g, int sidx, Gate &res) -> int {
         Op<real> &op = prog.op[n_ops++];
-        const Stage &st = prog.stage[pk.stage];
+        const Stage &st = prog.stage[sidx];
         const uint64_t ctrl_in = g.ctrl_mask & S;
         op.ctrl_out = g.ctrl_mask & ~S;
         uint32_t ct = 0; /* controls inside the tile, tile-bit coordinates */
@@ -352,12 +412,25 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 if (st.R[j] == tb) return j;
             return -1;
         };
+        /* tile offset of the element register r holds NOW (relabelled by the stage's shears) */
+        auto roff_of = [&](int r) {
+            const uint32_t logical = (uint32_t)r ^ flip;
+            uint32_t roff = 0;
+            for (int j = 0; j < K; ++j)
+                if (logical & (1u << j)) roff |= 1u << st.R[j];
+            return roff;
+        };
         op.tsel = 0;
         op.regsel = 0;
         op.bit = 0;
         op.mux_out = 0;
         op.code = 0;
+        int res_kind = 0;
         int mux_regbit = -1;
+        bool shear = false;
+        uint32_t mux_arm = 0;
+        const bool is_x = g.mux < 0 && g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
+                          g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.;
         if (gate_is_diag(g)) {
             const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
@@ -379,7 +452,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                     const int j = regbit(g.target);
                     if (j >= 0) {
                         for (int r = 0; r < (1 << K); ++r)
-                            if (r & (1 << j)) op.regsel |= 1u << r;
+                            if (((uint32_t)r ^ flip) & (1u << j)) op.regsel |= 1u << r;
                     } else {
                         op.tsel = 1u << lane_to_tile[g.target];
                     }
@@ -387,36 +460,112 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                     op.bit = g.target;
                 }
             }
-        } else if (g.mux < 0 && g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
-                   g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.) {
+        } else if (is_x) {
             op.kind = OP_SWAP;
             op.bit = regbit(g.target);
         } else {
             op.kind = OP_GEN;
-            op.bit = regbit(g.target);
-            for (int e = 0; e < 8; ++e) op.m[e] = (real)g.m[e];
-        }
-        uint32_t mux_arm = 0;
-        if (g.mux >= 0) {
-            /* multiplexed 2x2: which matrix a pair gets depends on one more lane */
-            for (int e = 0; e < 8; ++e) op.m1[e] = (real)g.m1[e];
-            if ((S >> g.mux) & 1ull) {
-                const int j = regbit(g.mux);
-                if (j >= 0) {
-                    mux_arm = ARM_MUX_REG;
-                    mux_regbit = j;
-                    for (int r = 0; r < (1 << K); ++r)
-                        if (r & (1 << j)) op.regsel |= 1u << r;
+            const int j = regbit(g.target);
+            op.bit = j;
+            /* the pair (a[r0], a[r0 | bit]) holds (q1, q0) when an earlier shear of this stage
+             * exchanged the outputs of register bit j: the gate then acts as P M P on it */
+            double m0[8], m1[8];
+            auto oriented = [&](const double *src, double *dst) {
+                if (flip & (1u << j)) {
+                    const int perm[4] = {3, 2, 1, 0};
+                    for (int e = 0; e < 4; ++e) dst[2 * e] = src[2 * perm[e]], dst[2 * e + 1] = src[2 * perm[e] + 1];
                 } else {
-                    mux_arm = ARM_MUX_THR;
-                    op.tsel = 1u << lane_to_tile[g.mux];
+                    std::memcpy(dst, src, 8 * sizeof(double));
+                }
+            };
+            oriented(g.m, m0);
+            if (g.mux >= 0) oriented(g.m1, m1);
+            if (g.mux >= 0) {
+                /* multiplexed 2x2: which matrix a pair gets depends on one more lane */
+                if ((S >> g.mux) & 1ull) {
+                    const int j2 = regbit(g.mux);
+                    if (j2 >= 0) {
+                        mux_arm = ARM_MUX_REG;
+                        mux_regbit = j2;
+                        for (int r = 0; r < (1 << K); ++r)
+                            if (r & (1 << j2)) op.regsel |= 1u << r;
+                        /* registers with bit j2 SET take the second matrix: under a relabelled j2
+                         * those hold the elements whose multiplexer bit is 0 */
+                        if (flip & (1u << j2)) {
+                            double t[8];
+                            std::memcpy(t, m0, sizeof(t));
+                            std::memcpy(m0, m1, sizeof(t));
+                            std::memcpy(m1, t, sizeof(t));
+                        }
+                    } else {
+                        mux_arm = ARM_MUX_THR;
+                        op.tsel = 1u << lane_to_tile[g.mux];
+                    }
+                } else {
+                    mux_arm = ARM_MUX_OUT;
+                    op.mux_out = g.mux;
+                }
+            }
+            /* three shears?  Exchanged outputs (s = 1) only where EVERY pair of every thread gets
+             * the gate: no controls, and both branches of a multiplexed gate agree on s */
+            ShearCoef c0[2], c1[2];
+            int s_pick = -1;
+            if (cfg.shear) {
+                double best = cfg.shear_max_coef;
+                const int s_hi = g.ctrl_mask == 0 ? 1 : 0;
+                for (int sx = 0; sx <= s_hi; ++sx) {
+                    if (!shear_factor(m0, sx, c0[sx])) continue;
+                    double worst = c0[sx].size;
+                    if (g.mux >= 0) {
+                        if (!shear_factor(m1, sx, c1[sx])) continue;
+                        worst = std::max(worst, c1[sx].size);
+                    }
+                    if (worst <= best) best = worst, s_pick = sx;
+                }
+            }
+            if (s_pick >= 0) {
+                shear = true;
+                op.kind = OP_SHEAR;
+                const ShearCoef &a0 = c0[s_pick];
+                const double k0[8] = {a0.y[0], a0.y[1], a0.g[0], a0.g[1], a0.x[0], a0.x[1], 0., 0.};
+                for (int e = 0; e < 8; ++e) op.m[e] = (real)k0[e];
+                double phi0[2] = {a0.phi[0], a0.phi[1]}, phi1[2] = {a0.phi[0], a0.phi[1]};
+                if (g.mux >= 0) {
+                    const ShearCoef &a1 = c1[s_pick];
+                    const double k1[8] = {a1.y[0], a1.y[1], a1.g[0], a1.g[1], a1.x[0], a1.x[1], 0., 0.};
+                    for (int e = 0; e < 8; ++e) op.m1[e] = (real)k1[e];
+                    phi1[0] = a1.phi[0], phi1[1] = a1.phi[1];
+                    if (mux_regbit >= 0 && (flip & (1u << mux_regbit))) std::swap(phi0[0], phi1[0]), std::swap(phi0[1], phi1[1]);
+                }
+                if (s_pick) flip ^= 1u << j;
+                /* the residual: phi on every amplitude the gate touched */
+                const bool trivial = phi0[0] == 1. && phi0[1] == 0. && phi1[0] == 1. && phi1[1] == 0.;
+                if (!trivial) {
+                    res = Gate();
+                    for (int e = 0; e < 8; ++e) res.m[e] = 0.;
+                    if (g.mux >= 0) { /* diag(phi0, phi1) on the multiplexer lane */
+                        res.target = g.mux;
+                        res.ctrl_mask = 0;
+                        res.m[0] = phi0[0], res.m[1] = phi0[1], res.m[6] = phi1[0], res.m[7] = phi1[1];
+                    } else if (g.ctrl_mask == 0) { /* a scalar: diag(phi, phi), any lane */
+                        res.target = g.target;
+                        res.ctrl_mask = 0;
+                        res.m[0] = res.m[6] = phi0[0], res.m[1] = res.m[7] = phi0[1];
+                    } else { /* controlled phase: one control lane becomes the target of diag(1, phi) */
+                        const int lane = __builtin_ctzll(g.ctrl_mask);
+                        res.target = lane;
+                        res.ctrl_mask = g.ctrl_mask & ~(1ull << lane);
+                        res.m[0] = 1., res.m[6] = phi0[0], res.m[7] = phi0[1];
+                    }
+                    res_kind = 1;
                 }
             } else {
-                mux_arm = ARM_MUX_OUT;
-                op.mux_out = g.mux;
+                for (int e = 0; e < 8; ++e) op.m[e] = (real)m0[e];
+                if (g.mux >= 0)
+                    for (int e = 0; e < 8; ++e) op.m1[e] = (real)m1[e];
             }
         }
-        if (op.kind == OP_GEN)
+        if (op.kind == OP_GEN || op.kind == OP_SHEAR)
             op.arm = ARM_GEN(op.bit) | mux_arm;
         else if (op.kind == OP_SWAP)
             op.arm = ARM_SWAP(op.bit);
@@ -427,18 +576,20 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         for (int j = 0; j < K; ++j) rmask |= 1u << st.R[j];
         op.cmt = ct & ~rmask;
         op.regmask = 0;
-        for (int r = 0; r < (1 << K); ++r) {
-            uint32_t roff = 0;
-            for (int j = 0; j < K; ++j)
-                if (r & (1 << j)) roff |= 1u << st.R[j];
-            if ((roff & ct & rmask) == (ct & rmask)) op.regmask |= 1u << r;
-        }
+        for (int r = 0; r < (1 << K); ++r)
+            if ((roff_of(r) & ct & rmask) == (ct & rmask)) op.regmask |= 1u << r;
         const uint32_t all_regs = (1u << K) >= 32 ? 0xffffffffu : ((1u << (1 << K)) - 1u);
-        if (op.kind == OP_GEN) {
+        if (op.kind == OP_GEN || op.kind == OP_SHEAR) {
             if (mux_regbit >= 0)
-                op.code = OPC_GEN_REGMUX(op.bit, mux_regbit);
+                op.code = shear ? OPC_SHEAR_REGMUX(op.bit, mux_regbit) : OPC_GEN_REGMUX(op.bit, mux_regbit);
+            else if (op.regmask == all_regs)
+                op.code = shear ? OPC_SHEAR(op.bit) : OPC_GEN(op.bit);
             else
-                op.code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
+                op.code = shear ? OPC_SHEAR_MASKED(op.bit) : OPC_GEN_MASKED(op.bit);
+            if (shear)
+                ++stats.shear_ops;
+            else
+                ++stats.direct_ops, ++prog.n_direct;
         } else if (op.kind == OP_SWAP) {
             op.code = OPC_SWAP(op.bit);
         } else {
@@ -459,10 +610,91 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 ref.pad_ = 0;
             }
         }
+        return res_kind;
+    };
+
+    /* D (diagonal, fresh from gate number pi of `picked`) -> into the next gate that acts
+     * non-diagonally on its lane.  Returns 0: folded away, 1: apply it now (the next such gate is
+     * controlled and runs in this pass), 2: no gate in this pass needs it applied first */
+    auto fold_forward = [&](const Gate &D, size_t pi) -> int {
+        const bool scalar = D.ctrl_mask == 0 && D.m[0] == D.m[6] && D.m[1] == D.m[7];
+        auto absorbs = [&](Gate &G) {
+            /* G <- G D: D acts first */
+            const double d[2][2] = {{D.m[0], D.m[1]}, {D.m[6], D.m[7]}};
+            auto scale_cols = [&](double *m) {
+                for (int row = 0; row < 2; ++row)
+                    for (int col = 0; col < 2; ++col) {
+                        double *e = &m[(row * 2 + col) * 2];
+                        const double re = e[0] * d[col][0] - e[1] * d[col][1];
+                        const double im = e[0] * d[col][1] + e[1] * d[col][0];
+                        e[0] = re, e[1] = im;
+                    }
+            };
+            scale_cols(G.m);
+            if (G.mux >= 0) scale_cols(G.m1);
+        };
+        auto visit = [&](Gate &G, bool in_pass) -> int { /* -1: keep looking */
+            if (gate_is_diag(G)) return -1;
+            if (scalar) {
+                if (G.ctrl_mask != 0) return -1; /* a scalar commutes with everything: look further */
+                absorbs(G);
+                return 0;
+            }
+            /* D is diagonal on its target and on its controls */
+            if (!(((D.ctrl_mask | (1ull << D.target)) >> G.target) & 1ull)) return -1;
+            if (G.ctrl_mask == 0 && D.ctrl_mask == 0) {
+                absorbs(G);
+                return 0;
+            }
+            return in_pass ? 1 : 2;
+        };
+        for (size_t k = pi + 1; k < picked.size(); ++k) {
+            const int r = visit(queue[picked[k].queue_idx], true);
+            if (r >= 0) return r;
+        }
+        for (size_t k = 0; k < queue.size(); ++k) {
+            if (is_picked[k]) continue;
+            const int r = visit(queue[k], false);
+            if (r >= 0) return r;
+        }
+        return 2;
+    };
+
+    bool any_unpicked = picked.size() < queue.size();
+    for (size_t pi = 0; pi < picked.size(); ++pi) {
+        const Picked &pk = picked[pi];
+        while (cur_stage < pk.stage) {
+            if (cur_stage >= 0) close_stage(cur_stage);
+            ++cur_stage;
+            prog.stage[cur_stage].op_begin = (int16_t)n_ops;
+            flip = 0;
+        }
+        Gate res;
+        const Gate g = queue[pk.queue_idx]; /* (a copy: residuals may rewrite later queue entries) */
+        if (lower(g, pk.stage, res)) {
+            const int where = fold_forward(res, pi);
+            if (where == 1 || (where == 2 && !any_unpicked)) {
+                /* apply the phase here, as a diagonal op of this stage (where == 1: the slot was
+                 * reserved when the gate was picked; otherwise only if the pass has room) */
+                Gate none;
+                const int still_to_come = (int)(picked.size() - pi - 1);
+                if (where == 1 || (n_ops + still_to_come < op_limit && n_ops + still_to_come < QGB_MAX_OPS)) {
+                    lower(res, pk.stage, none);
+                    ++stats.residual_ops;
+                } else {
+                    deferred.push_back(res);
+                }
+            } else if (where == 2) {
+                deferred.push_back(res);
+            }
+        }
     }
-    if (cur_stage >= 0) prog.stage[cur_stage].op_end = (int16_t)n_ops;
-    for (int s = cur_stage + 1; s < n_stages; ++s)
+    if (cur_stage >= 0) close_stage(cur_stage);
+    for (int s = cur_stage + 1; s < n_stages; ++s) {
         prog.stage[s].op_begin = prog.stage[s].op_end = (int16_t)n_ops;
+        prog.stage[s].store_flip = 0;
+        prog.stage[s].store_xor = 0;
+    }
     prog.n_ops = n_ops;
 
     /* drop the executed gates, keep the rest in order */
@@ -476,6 +708,8 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 ++w;
             }
         queue.resize(w);
+        /* phases nothing could absorb: their place is right after this pass */
+        if (!deferred.empty()) queue.insert(queue.begin(), deferred.begin(), deferred.end());
     }
     stats.gates_in_pass = (int)picked.size();
     stats.ops_in_pass = n_ops;

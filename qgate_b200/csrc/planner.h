@@ -25,12 +25,20 @@ struct PlanConfig {
     /* give runs of consecutive stages the same warp-index bits (tile bits none of them uses as a
      * register bit) so that a stage transition needs a warp barrier only (Stage::warp_local) */
     bool warp_local = false;
+    /* lower dense 2x2 gates as three in-place complex shears (OP_SHEAR, program.h) where the
+     * factorisation is well conditioned (every coefficient <= shear_max_coef in magnitude);
+     * the rest stays a direct 2x2 (OP_GEN) */
+    bool shear = false;
+    double shear_max_coef = 12.;
 };
 
 struct PlanStats {
     int gates_in_pass = 0;
     int ops_in_pass = 0;
     int stages_in_pass = 0;
+    int shear_ops = 0;    /* dense gates lowered as OP_SHEAR                                  */
+    int direct_ops = 0;   /* dense gates lowered as OP_GEN (direct 2x2)                       */
+    int residual_ops = 0; /* diagonal ops added for phases no later gate could absorb          */
 };
 
 /* merge `g` into the queue: an uncontrolled gate folds into the previous gate on the same

@@ -27,6 +27,13 @@ enum OpKind : int {
     OP_DIAG_OUT = 3, /* diag on a lane OUTSIDE the tile (`bit` = state-vector lane): the CTA  */
                      /* picks d0 or d1 from its base index                                    */
     OP_SWAP = 5,     /* exchange the two amplitudes of register bit `bit` (X, CX, CCX ...)    */
+    OP_SHEAR = 6,    /* 2x2 on register bit `bit` as THREE complex shears, in place:           */
+                     /*   q0 += y q1;  q1 += g q0;  q0 += x q1        (m = y, g, x, 0)          */
+                     /* = N q for the unit-determinant matrix N = [[1,x],[0,1]] [[1,0],[g,1]]   */
+                     /* [[1,y],[0,1]].  The planner writes a gate matrix M as phi * P^s * N     */
+                     /* (P = exchange of the two outputs): phi goes into a later gate or a      */
+                     /* diagonal op, P is a RELABELLING of the stage's registers (Stage::      */
+                     /* store_flip) — 12 FMAs per pair instead of 16 and no temporaries.       */
 };
 
 /* Op::arm bits: GEN on register bit j = 1 << j, SWAP on register bit j = 16 << j */
@@ -78,6 +85,11 @@ struct Op {
 #define OPC_SWAP(j) (24 + (j))
 #define OPC_DIAG_REG 28
 #define OPC_DIAG_THR 29
+#define OPC_SHEAR(j) (32 + (j))                     /* three shears on register bit j (m, or m1    */
+                                                    /* where a thread-bit / outside multiplexer is 1) */
+#define OPC_SHEAR_MASKED(j) (36 + (j))              /* the same under register-bit controls (regmask) */
+#define OPC_SHEAR_REGMUX(j, j2) (40 + 4 * (j) + (j2)) /* multiplexed by register bit j2               */
+#define OPC_COUNT 56
 
 /* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
  * (byte address bits [6:4] ^= bits [9:7]).  Linear over GF(2), so
@@ -100,6 +112,12 @@ struct Stage {
     uint16_t sro[1 << QGB_MAX_REG_BITS];  /* swizzled tile offset of register index r       */
     uint32_t xb[QGB_MAX_REG_BITS];        /* swizzled BYTE offset of register bit j: the slot of */
                                           /* register r is base ^ XOR of xb[j] over the bits of r */
+    /* Register relabelling accumulated by the stage's OP_SHEAR ops (exchanged outputs): at the end
+     * of the stage register r holds the tile element of register index r ^ store_flip, i.e. it is
+     * stored at slot ^ store_xor (store_xor = XOR of xb[j] over the bits of store_flip).  The
+     * planner has already expressed every later op of the stage in relabelled registers. */
+    uint32_t store_flip;
+    uint32_t store_xor;
 };
 
 template <typename real>
@@ -122,6 +140,7 @@ struct PassProgram {
     /* ops that look at lanes OUTSIDE the tile (controls, multiplexer, diagonal target): the
      * TMA-staged kernel turns them into two per-tile bit masks over the ops instead of testing
      * every op of every tile (needs n_ops <= 32) */
+    int32_t n_direct;     /* OP_GEN ops (direct 2x2, the fallback of OP_SHEAR): 0 -> the leaner kernel variant */
     int32_t n_out;
     struct OutRef {
         uint64_t ctrl_mask;   /* the op runs only in tiles whose origin has these bits set       */

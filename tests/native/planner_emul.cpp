@@ -24,6 +24,7 @@ static int g_failures = 0;
 static bool g_expect_tma = false;
 static long g_warp_local = 0;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
+static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
         if (!(cond)) {                        \
@@ -64,7 +65,7 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
         for (int o = 0; o < p.n_ops; ++o) {
             const Op<real> &op = p.op[o];
             int lane = -1;
-            if (op.kind == OP_GEN && (op.arm & ARM_MUX_OUT)) lane = op.mux_out;
+            if ((op.kind == OP_GEN || op.kind == OP_SHEAR) && (op.arm & ARM_MUX_OUT)) lane = op.mux_out;
             if (op.kind == OP_DIAG_OUT) lane = op.bit;
             if (op.kind == OP_DIAG || op.kind == OP_DIAG_OUT)
                 CHECK(op.m1[0] == op.m[2] && op.m1[1] == op.m[3], "diag op %d: d1 not mirrored into m1", o);
@@ -177,23 +178,27 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     CHECK((op.cmt & rmask) == 0, "thread-part controls overlap the register bits");
                     {
                         uint32_t want = 0;
-                        if (op.kind == OP_GEN) want = ARM_GEN(op.bit) | (op.arm & (ARM_MUX_THR | ARM_MUX_REG | ARM_MUX_OUT));
+                        if (op.kind == OP_GEN || op.kind == OP_SHEAR) want = ARM_GEN(op.bit) | (op.arm & (ARM_MUX_THR | ARM_MUX_REG | ARM_MUX_OUT));
                         else if (op.kind == OP_SWAP) want = ARM_SWAP(op.bit);
                         else want = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
                         CHECK(op.arm == want, "arm selector %u of op kind %d bit %d", op.arm, op.kind, op.bit);
                         /* Op::code, the body selector of the TMA-staged kernel */
                         const uint32_t all_regs = (1u << (1 << K)) - 1u;
                         int code = -1;
-                        if (op.kind == OP_GEN && (op.arm & ARM_MUX_REG)) {
+                        const bool sh = op.kind == OP_SHEAR;
+                        if ((op.kind == OP_GEN || sh) && (op.arm & ARM_MUX_REG)) {
                             for (int j2 = 0; j2 < K; ++j2) {
                                 uint32_t sel = 0;
                                 for (int r = 0; r < (1 << K); ++r)
                                     if (r & (1 << j2)) sel |= 1u << r;
-                                if (sel == op.regsel) code = OPC_GEN_REGMUX(op.bit, j2);
+                                if (sel == op.regsel) code = sh ? OPC_SHEAR_REGMUX(op.bit, j2) : OPC_GEN_REGMUX(op.bit, j2);
                             }
                             CHECK(op.regmask == all_regs && op.cmt == 0 && op.ctrl_out == 0, "multiplexed op with controls");
-                        } else if (op.kind == OP_GEN) {
-                            code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
+                        } else if (op.kind == OP_GEN || sh) {
+                            if (sh)
+                                code = op.regmask == all_regs ? OPC_SHEAR(op.bit) : OPC_SHEAR_MASKED(op.bit);
+                            else
+                                code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
                         } else if (op.kind == OP_SWAP) {
                             code = OPC_SWAP(op.bit);
                         } else {
@@ -204,7 +209,32 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     const bool active = (ebase & op.cmt) == op.cmt;
                     const cd m0(op.m[0], op.m[1]), m1(op.m[2], op.m[3]), m2(op.m[4], op.m[5]),
                         m3(op.m[6], op.m[7]);
-                    if (op.kind == OP_GEN || op.kind == OP_SWAP) {
+                    if (op.kind == OP_SHEAR) {
+                        /* q0 += y q1; q1 += g q0; q0 += x q1 on the pairs of register bit `bit`, exactly
+                         * as kernels_tma.cu does it (in place, in `real`) */
+                        CHECK(op.bit >= 0 && op.bit < K, "register bit %d out of range", op.bit);
+                        ++g_shear;
+                        for (int r0 = 0; r0 < (1 << K); ++r0) {
+                            if (r0 & (1 << op.bit)) continue;
+                            const int r1 = r0 | (1 << op.bit);
+                            if (!((op.regmask >> r0) & 1u) || !active) continue;
+                            bool one = false;
+                            if (op.arm & ARM_MUX_THR) one = (ebase & op.tsel) != 0;
+                            if (op.arm & ARM_MUX_REG) one = (op.regsel >> r0) & 1u;
+                            if (op.arm & ARM_MUX_OUT) one = (base >> op.mux_out) & 1ull;
+                            if (tid == 0 && r0 == 0 && bid == 0) {
+                                g_mux_thr += (op.arm & ARM_MUX_THR) != 0;
+                                g_mux_reg += (op.arm & ARM_MUX_REG) != 0;
+                                g_mux_out += (op.arm & ARM_MUX_OUT) != 0;
+                            }
+                            const real *k = one ? op.m1 : op.m;
+                            const cd y(k[0], k[1]), g(k[2], k[3]), x(k[4], k[5]);
+                            a[r0] += y * a[r1];
+                            a[r1] += g * a[r0];
+                            a[r0] += x * a[r1];
+                        }
+                    } else if (op.kind == OP_GEN || op.kind == OP_SWAP) {
+                        if (op.kind == OP_GEN) ++g_direct;
                         CHECK(op.bit >= 0 && op.bit < K, "register bit %d out of range", op.bit);
                         for (int r0 = 0; r0 < (1 << K); ++r0) {
                             if (r0 & (1 << op.bit)) continue;
@@ -254,7 +284,12 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                         CHECK(false, "unknown op kind %d", op.kind);
                     }
                 }
-                for (int r = 0; r < (1 << K); ++r) tile[ebase | roff(r)] = a[r];
+                /* registers relabelled by the stage's shears go back to the slots they now stand for */
+                uint32_t sx = 0;
+                for (int j = 0; j < K; ++j)
+                    if (st.store_flip & (1u << j)) sx ^= st.xb[j];
+                CHECK(sx == st.store_xor && st.store_flip < (1u << K), "stage %d: store_xor disagrees with store_flip", s);
+                for (int r = 0; r < (1 << K); ++r) tile[ebase | roff(r ^ (int)st.store_flip)] = a[r];
             }
             for (uint32_t e = 0; e < tile_size; ++e)
                 if (seen[e] != 1) {
@@ -308,7 +343,7 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
 
 template <typename real>
 static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops, int max_stages,
-                     bool merge, uint64_t seed, bool tma = false, int reg_bits = 0, int max_cost = 0) {
+                     bool merge, uint64_t seed, bool tma = false, int reg_bits = 0, int max_cost = 0, bool shear = false) {
     std::mt19937_64 rng(seed);
     std::vector<cd> ref(1ull << n), amp;
     std::normal_distribution<double> nd;
@@ -330,6 +365,7 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     cfg.max_ops = max_ops;
     cfg.max_stages = max_stages;
     cfg.warp_local = tma;
+    cfg.shear = shear;
     if (tma) { /* what engine.cu sets for the TMA-staged kernel */
         cfg.row_lanes = cfg.fp32 ? 4 : 3;
         cfg.max_groups = QGB_MAX_GROUPS;
@@ -337,20 +373,25 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     }
     g_expect_tma = tma && n > cfg.row_lanes && std::min(T, n) >= cfg.row_lanes;
     static PassProgram<real> prog;
-    int n_pass = 0, n_exec = 0;
+    int n_pass = 0, n_exec = 0, n_deferred = 0;
     while (!queue.empty()) {
         const size_t before = queue.size();
         PlanStats st;
         plan_pass<real>(queue, n, cfg, prog, st);
-        CHECK(queue.size() < before, "planner made no progress");
-        if (queue.size() >= before) return;
-        CHECK((int)(before - queue.size()) == st.gates_in_pass, "gate accounting");
+        /* (a pass may hand back one phase gate per sheared gate it executed: count gates, not queue length) */
+        CHECK(st.gates_in_pass > 0 && n_pass < 100000, "planner made no progress");
+        if (st.gates_in_pass <= 0 || n_pass >= 100000) return;
+        CHECK(queue.size() + st.gates_in_pass >= before, "gate accounting");
         CHECK(prog.n_ops <= max_ops && prog.n_stages <= std::max(1, max_stages), "limits exceeded");
         emulate_pass<real>(prog, amp);
         ++n_pass;
         n_exec += st.gates_in_pass;
+        n_deferred += (int)queue.size() - ((int)before - st.gates_in_pass);
+        g_residual_ops += st.residual_ops;
+        for (int s = 0; s < prog.n_stages; ++s) g_flipped_stages += prog.stage[s].store_flip != 0;
+        CHECK(shear || (st.shear_ops == 0 && st.residual_ops == 0), "shear ops planned without the option");
     }
-    CHECK(n_exec + n_merged == n_gates, "executed %d + merged %d != %d", n_exec, n_merged, n_gates);
+    CHECK(n_exec + n_merged == n_gates + n_deferred, "executed %d + merged %d != %d + %d deferred phases", n_exec, n_merged, n_gates, n_deferred);
     double err = 0., scale = 0.;
     for (size_t i = 0; i < ref.size(); ++i) {
         err = std::max(err, std::abs(ref[i] - amp[i]));
@@ -358,8 +399,9 @@ static void run_case(int n, int T, int L, int n_gates, int max_ctrl, int max_ops
     }
     const double tol = sizeof(real) == 4 ? 2e-4 : 1e-11; /* op matrices are rounded to `real` */
     CHECK(err <= tol * scale, "n=%d T=%d L=%d gates=%d: rel err %.3g", n, T, L, n_gates, err / scale);
-    std::printf("ok %s n=%2d T=%2d L=%d gates=%4d passes=%3d merged=%3d relerr=%.2e%s\n",
-                sizeof(real) == 4 ? "f32" : "f64", n, T, L, n_gates, n_pass, n_merged, err / scale, tma ? " tma" : "");
+    std::printf("ok %s n=%2d T=%2d L=%d gates=%4d passes=%3d merged=%3d relerr=%.2e%s%s\n",
+                sizeof(real) == 4 ? "f32" : "f64", n, T, L, n_gates, n_pass, n_merged, err / scale, tma ? " tma" : "",
+                shear ? " shear" : "");
 }
 
 int main() {
@@ -389,7 +431,17 @@ int main() {
         run_case<double>(n, 11, 3, 300, 9, 32, QGB_MAX_STAGES, true, seed++, true, 4, 32);
         run_case<float>(n, 11, 6, 120, 3, 32, QGB_MAX_STAGES, true, seed++, true, 4, 24);
     }
+    /* dense gates as three in-place shears (OP_SHEAR): relabelled registers, folded phases */
+    for (int n : {9, 10, 12, 14}) {
+        for (int ctrl : {0, 1, 3}) {
+            run_case<double>(n, 10, 5, 300, ctrl, 32, QGB_MAX_STAGES, true, seed++, true, 4, 24, true);
+            run_case<double>(n, 9, 3, 250, ctrl, 32, QGB_MAX_STAGES, false, seed++, true, 3, 48, true);
+            run_case<float>(n, 11, 6, 100, ctrl, 32, QGB_MAX_STAGES, true, seed++, true, 4, 24, true);
+        }
+        run_case<double>(n, 10, 5, 300, 2, 6, 3, true, seed++, true, 4, 0, true);
+    }
     g_expect_tma = false;
+    run_case<double>(11, 8, 3, 400, 2, 16, 3, true, seed++, false, 0, 0, true);
     /* limits and no-merge paths */
     run_case<double>(10, 7, 2, 300, 3, 5, QGB_MAX_STAGES, false, seed++);
     run_case<double>(10, 7, 2, 300, 3, QGB_MAX_OPS, 2, true, seed++);
@@ -403,6 +455,12 @@ int main() {
                 g_mux_out);
     if (g_mux_thr == 0 || g_mux_reg == 0 || g_mux_out == 0) {
         std::printf("FAIL: a multiplexer placement was never exercised\n");
+        return 1;
+    }
+    std::printf("shear ops %ld, direct 2x2 ops %ld, stages stored through a relabelling %ld, residual phase ops %ld\n",
+                g_shear, g_direct, g_flipped_stages, g_residual_ops);
+    if (g_shear == 0 || g_direct == 0 || g_flipped_stages == 0 || g_residual_ops == 0) {
+        std::printf("FAIL: a shear path was never exercised\n");
         return 1;
     }
     std::printf("warp-local stage transitions checked: %ld\n", g_warp_local);

@@ -28,8 +28,9 @@ def default_options(cuda_runtime):
     api = cuda_runtime.get_api()
     for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 11),
                         ('low_lanes_fp64', 0), ('low_lanes_fp32', 0), ('max_gates_per_pass', 112), ('max_cost', 0),
-                        ('tma', 1), ('tma_buffers', 0), ('tile_buffers', 1), ('reg_bits_fp64', 4),
-                        ('ctas_per_sm', 0), ('tma_ws', 0), ('warp_local', 0)):
+                        ('tma_buffers', 0), ('reg_bits_fp64', 4), ('ctas_per_sm', 0), ('tma_ws', 0),
+                        ('warp_local', 0), ('shear_fp64', 1), ('shear_fp32', 1), ('exact', 0), ('l2_hint', 0),
+                        ('debug_pass_mode', 0)):
         api.set_option(name, value)
     yield
 
@@ -321,32 +322,41 @@ def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
     lanes = 'tile_lanes_fp64' if dtype is np.float64 else 'tile_lanes_fp32'
     low = 'low_lanes_fp64' if dtype is np.float64 else 'low_lanes_fp32'
     k = 3 if dtype is np.float64 else 4
-    # both staging engines (TMA tensor-map copies / cp.async) over every tile shape
-    for tma, buffers in ((1, 2), (1, 3), (0, 1), (0, 2)):
-        for t in (k + 5, k + 6, k + 8, k + 9, k + 10):
-            for l in (1, 3, 6):
-                shapes.append({'fuse': 1, 'tma': tma, 'tma_buffers' if tma else 'tile_buffers': buffers,
-                               lanes: t, low: l})
-    shapes.append(dict(fuse=1, tma=1, max_gates_per_pass=3))
+    # every tile shape, 2 and 3 tile buffers, dense gates as direct 2x2 products and as shears
+    for shear in (0, 1):
+        for buffers in (2, 3):
+            for t in (k + 5, k + 6, k + 8, k + 9, k + 10):
+                for l in (1, 3, 6):
+                    shapes.append({'fuse': 1, 'shear': shear, 'tma_buffers': buffers, lanes: t, low: l})
+    shapes.append(dict(fuse=1, shear=1, max_gates_per_pass=3))
+    shapes.append(dict(fuse=1, shear=0, max_gates_per_pass=3))
+    for l2_hint in (1, 2, 3):
+        shapes.append(dict(fuse=1, shear=1, max_gates_per_pass=112, l2_hint=l2_hint))
     for ws_buffers in (2, 3):                        # the warp-specialised variant (producer warp)
         for t in (k + 5, k + 7, k + 8, k + 9):
-            shapes.append({'fuse': 1, 'tma': 1, 'tma_ws': 1, 'tma_buffers': ws_buffers, lanes: t, low: 0})
-    shapes.append({'fuse': 1, 'tma': 1, 'tma_ws': 0, 'tma_buffers': 0, lanes: k + 8, low: 0})
+            shapes.append({'fuse': 1, 'shear': 1, 'l2_hint': 0, 'tma_ws': 1, 'tma_buffers': ws_buffers, lanes: t, low: 0})
+    shapes.append({'fuse': 1, 'tma_ws': 0, 'tma_buffers': 0, lanes: k + 8, low: 0})
     for t in (k + 6, k + 7, k + 8, k + 9):           # warp-local stage transitions
-        shapes.append({'fuse': 1, 'tma': 1, 'warp_local': 1, lanes: t, low: 0})
-    shapes.append({'fuse': 1, 'tma': 1, 'warp_local': 0, lanes: k + 6, low: 0})
+        shapes.append({'fuse': 1, 'warp_local': 1, lanes: t, low: 0})
+    shapes.append({'fuse': 1, 'warp_local': 0, lanes: k + 6, low: 0})
     if dtype is np.float64:
         for t in (8, 9, 11, 12):
-            shapes.append(dict(fuse=1, tma=1, tma_buffers=2, reg_bits_fp64=3, tile_lanes_fp64=t, low_lanes_fp64=5))
+            for shear in (0, 1):
+                shapes.append(dict(fuse=1, shear=shear, tma_buffers=2, reg_bits_fp64=3, tile_lanes_fp64=t, low_lanes_fp64=5))
     for options in shapes:
         api.stats_reset()
+        options.setdefault('shear_fp64', 1)
+        options.setdefault('shear_fp32', 1)
+        if 'shear' in options:       # (sets both precisions)
+            options['shear_fp64'] = options['shear_fp32'] = options.pop('shear')
         got = run(**options)
         assert cases.rel_err(got, base) < tol, options
         stats = api.stats()
-        if options.get('tma', 1):
-            assert stats['tma_passes'] == stats['tile_passes'] > 0, (options, stats)
+        assert stats['tma_passes'] == stats['tile_passes'] > 0, (options, stats)
+        if options['shear_fp64' if dtype is np.float64 else 'shear_fp32']:
+            assert stats['shear_ops'] > 10 * stats['direct_ops'], (options, stats)
         else:
-            assert stats['tma_passes'] == 0 and stats['tile_passes'] > 0, (options, stats)
+            assert stats['shear_ops'] == 0 and stats['direct_ops'] > 0, (options, stats)
 
 
 @pytest.mark.parametrize('dtype,n', ((np.float64, 27), (np.float32, 28)))
