@@ -58,6 +58,10 @@ def parse_args():
                     help='gates of layer 0 the CPU reference runs per step (45 = the whole layer at 30 qubits, ~12 s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the sub-records (the other precision, the QFT runs)')
+    ap.add_argument('--own-frontend', action='store_true',
+                    help="e2e through this package's front end even when the reference's is installed")
     ap.add_argument('--option', action='append', default=[], help='engine option name=value')
     ap.add_argument('--exchange', default='auto', choices=('auto', 'p2p', 'collective'),
                     help='lane exchange engine of the sharded runs')
@@ -263,6 +267,129 @@ def submit_native(proc, qstates, gates):
             check(rc)
 
 
+# FP64 / FP32 issue ceilings of the dense-gate arithmetic (tools/dfma_probe.cu on B200: one DFMA warp
+# instruction per 2.1 cycles per SM partition; packed FFMA2: one per cycle), at the maximum SM clock
+def pipe_roofline(dtype_name, stats, n_local, seconds, sm_max_mhz):
+    sm_count, partitions = 148, 4
+    clock = (sm_max_mhz or 1965.) * 1e6
+    if dtype_name == 'f64':
+        per_amp_shear, per_amp_direct, rate, unit = 6., 8., 32. / 2.1, 'DFMA/s'
+    else:
+        per_amp_shear, per_amp_direct, rate, unit = 3., 4., 32., 'FFMA2/s'
+    instr = (per_amp_shear * stats.get('shear_ops', 0) + per_amp_direct * stats.get('direct_ops', 0)) \
+        * float(1 << n_local)
+    peak = sm_count * partitions * rate * clock
+    achieved = instr / seconds if seconds > 0 else 0.
+    return {'achieved': achieved, 'peak': peak, 'unit': unit, 'frac': achieved / peak,
+            'per_amplitude': {'sheared 2x2': per_amp_shear, 'direct 2x2': per_amp_direct},
+            'sheared_ops': stats.get('shear_ops', 0), 'direct_ops': stats.get('direct_ops', 0),
+            'peak_source': 'tools/dfma_probe.cu issue rate x {:.0f} MHz'.format(clock / 1e6)}
+
+
+def device_leg(args, dtype_name, n, gates, runtime, api, torch, dist, distributed, stream, steps, warmup,
+               sample_clocks, local_rank):
+    """gates queued in the engine, CUDA events around the flush; returns the numbers of one dtype"""
+    dtype = np.float64 if dtype_name == 'f64' else np.float32
+    elem = 16 if dtype_name == 'f64' else 8
+    upd = updates_of(gates, n)
+    qstates = runtime.create_qubit_states(dtype)
+    proc = qstates.processor
+    proc.initialize_qubit_states(qstates, n)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def device_step():
+        proc.reset_qubit_states(qstates)
+        if distributed:
+            proc.submit_tuples(qstates, gates)
+        else:
+            submit_native(proc, qstates, gates)
+
+    for _ in range(warmup):
+        device_step()
+        proc.flush(qstates)
+    barrier()
+    api.stats_reset()
+    if distributed:
+        runtime.ctx.exchange_ms()
+        for key in runtime.ctx.stats:
+            runtime.ctx.stats[key] = 0
+    clocks = ClockSampler(local_rank) if sample_clocks else None
+    if clocks:
+        clocks.start()
+    device_ms = 0.
+    for _ in range(steps):
+        device_step()
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            proc.flush(qstates)
+            ev1.record(stream)
+        barrier()
+        device_ms += ev0.elapsed_time(ev1)
+    clock_info = clocks.stop() if clocks else None
+    stats = api.stats()
+    p0 = proc.calc_probability(qstates, 0)     # keeps the result observable
+    if distributed:
+        t = torch.tensor([device_ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        device_ms = float(t.item())
+    exch_ms = runtime.ctx.exchange_ms() if distributed else 0.
+    dstats = dict(runtime.ctx.stats) if distributed else None
+    qstates.delete()
+    del qstates, proc
+    n_local = n - int(round(math.log2(max(1, int(os.environ.get('WORLD_SIZE', '1'))))))
+    tile_passes = stats['tile_passes']
+    pass_bytes = 2 * (elem << n_local)
+    avg_pass_ms = (device_ms - exch_ms) / max(1, tile_passes)
+    peak, peak_src = measured_peak()
+    achieved = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
+    kernel_name = 'tma_pass_kernel'
+    pipe = pipe_roofline(dtype_name, stats, n_local, (device_ms - exch_ms) * 1e-3,
+                         clock_info['sm_max_mhz'] if clock_info else None)
+    roofline = {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': measured_traffic(dtype_name, n_local, kernel_name),
+                'peak_source': peak_src, 'bytes_per_launch': pass_bytes,
+                'avg_launch_ms': avg_pass_ms, 'launches_per_step': tile_passes / steps,
+                'gates_per_launch': len(gates) * steps / max(1, tile_passes),
+                'dense_ops_per_launch': (stats.get('shear_ops', 0) + stats.get('direct_ops', 0)) / max(1, tile_passes),
+                # a pass that fuses many dense gates is bound by the FP pipe, not by HBM: both
+                # fractions are reported, the larger one names the binding roofline
+                'fp64_pipe_frac' if dtype_name == 'f64' else 'fp32_pipe_frac': pipe['frac'],
+                'pipe': pipe}
+    return {'value': upd * steps / (device_ms * 1e-3), 'device_ms': device_ms, 'stats': stats,
+            'clocks': clock_info, 'roofline': roofline, 'p0': p0, 'exch_ms': exch_ms, 'dstats': dstats,
+            'updates': upd}
+
+
+def qft_records(n_gpus, g_bits, dtype_name, rank):
+    """The other half of BASELINE.json's metric: QFT time.  At N GPUs: QFT-(30 + log2 N) (16 GiB per
+    GPU, the bench shard) and the largest QFT that fits N GPUs up to 35 qubits (128 GiB per GPU at
+    N = 1, 2, 4; 64 GiB at N = 8), each checked against the closed form of QFT|5> and P(0) = 1/2 of
+    every qubit (run_configs.py)."""
+    import run_configs
+    import torch
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    records = []
+    for n in sorted({30 + g_bits, min(33 + g_bits, 35)}):
+        qargs = argparse.Namespace(qubits=n, dtype=dtype_name)
+        try:
+            rec = run_configs.run_qft(qargs, torch, world, rank)
+            records.append({'qubits': n, 'gates': rec['gates'], 'state_bytes_per_gpu': rec['state_bytes'] // n_gpus,
+                            'ms': 1e3 * rec['run_s'], 'all_qubit_p0_ms': 1e3 * rec['calc_probability_all_s'],
+                            'amplitude_rel_err_vs_closed_form': rec['amplitude_rel_err_vs_closed_form'],
+                            'p0_max_abs_err': rec['p0_max_abs_err'], 'ok': rec['ok']})
+        except Exception as exc:   # e.g. not enough free device memory for the 128 GiB case
+            records.append({'qubits': n, 'ok': False, 'error': str(exc)[:200]})
+    return records
+
+
 def main():
     args = parse_args()
     dtype = np.float64 if args.dtype == 'f64' else np.float32
@@ -286,8 +413,17 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        # the CPU arm runs the single-GPU problem size: one host has to hold the whole state
+        # the CPU arm runs the single-GPU problem size: one host has to hold the whole state and
+        # sweep it once per gate.  Its line names what it ran.
         n_ref = min(n, args.qubits)
+        if n_ref != n:
+            config = dict(config)
+            config['workload'] = config['workload'].replace('{} qubits'.format(n), '{} qubits'.format(n_ref))
+            config['qubits'] = n_ref
+            config['sharding'] = 'none (host memory)'
+            config['note'] = ('the GPU arm at {} GPUs runs {} qubits (weak scaling, {} per GPU); the CPU arm '
+                              'runs the 1-GPU size, {} qubits: updates/s is a rate, the sizes differ'
+                              .format(n_gpus, n, args.qubits, n_ref))
         value, ms, desc = run_reference_arm(args, dtype, n_ref)
         line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
                 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
@@ -322,8 +458,6 @@ def main():
     gates = random_circuit_gates(n, args.depth, args.seed)
     upd = updates_of(gates, n)
 
-    clocks = ClockSampler(local_rank)
-
     def barrier():
         torch.cuda.synchronize()
         if distributed:
@@ -338,67 +472,20 @@ def main():
         runtime.ctx.timing = True
         stream = runtime.ctx.stream
     else:
+        dist = None
         runtime = cudaruntime
+        cudaruntime.module_init() if not cudaruntime.initialized else None
         stream = torch.cuda.Stream()
-    qstates = runtime.create_qubit_states(dtype)
-    proc = qstates.processor
-    proc.initialize_qubit_states(qstates, n)
-    if not distributed:
         api.set_stream(stream.cuda_stream)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-
-    def device_step():
-        proc.reset_qubit_states(qstates)
-        if distributed:
-            proc.submit_tuples(qstates, gates)
-        else:
-            submit_native(proc, qstates, gates)
-
-    for _ in range(args.warmup):
-        device_step()
-        proc.flush(qstates)
-    barrier()
-    api.stats_reset()
-    if distributed:
-        runtime.ctx.exchange_ms()
-        for key in runtime.ctx.stats:
-            runtime.ctx.stats[key] = 0
-    clocks.start()
-    device_ms = 0.
-    for _ in range(args.steps):
-        device_step()
-        barrier()
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            proc.flush(qstates)
-            ev1.record(stream)
-        barrier()
-        device_ms += ev0.elapsed_time(ev1)
-    clock_info = clocks.stop()
-    stats = api.stats()
-    p0 = proc.calc_probability(qstates, 0)     # keeps the result observable
-    if distributed:
-        t = torch.tensor([device_ms], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        device_ms = float(t.item())
-    value = upd * args.steps / (device_ms * 1e-3)
-    tile_passes = stats['tile_passes']
+    leg = device_leg(args, args.dtype, n, gates, runtime, api, torch, dist, distributed, stream, args.steps,
+                     args.warmup, True, local_rank)
+    value, device_ms, stats, clock_info = leg['value'], leg['device_ms'], leg['stats'], leg['clocks']
+    roofline, p0, exch_ms = leg['roofline'], leg['p0'], leg['exch_ms']
+    achieved = roofline['achieved']
     launches = stats['kernel_launches']
-    pass_bytes = 2 * (elem << args.qubits)
-    exch_ms = runtime.ctx.exchange_ms() if distributed else 0.
-    avg_pass_ms = (device_ms - exch_ms) / max(1, tile_passes)
-    peak, peak_src = measured_peak()
-    achieved = pass_bytes / (avg_pass_ms * 1e-3) / 1e9
-    kernel_name = 'tma_pass_kernel' if stats.get('tma_passes', 0) == tile_passes else 'tile_pass_kernel'
-    roofline = {'bound': 'hbm', 'kernel': kernel_name, 'achieved': achieved, 'peak': peak,
-                'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': measured_traffic(args.dtype, args.qubits, kernel_name),
-                'peak_source': peak_src, 'bytes_per_launch': pass_bytes,
-                'avg_launch_ms': avg_pass_ms, 'launches_per_step': tile_passes / args.steps,
-                'gates_per_launch': len(gates) * args.steps / max(1, tile_passes)}
     nvlink = None
     if distributed:
-        dstats = runtime.ctx.stats
+        dstats = leg['dstats']
         if dstats['exchanges']:
             # bytes each GPU sends (= receives) per exchange over its NVLink ports
             gbs = dstats['exchange_bytes'] / (exch_ms * 1e-3) / 1e9
@@ -409,15 +496,48 @@ def main():
                       'ms_per_step': exch_ms / args.steps, 'achieved': gbs, 'unit': 'GB/s',
                       'peak': 770., 'frac': gbs / 770.,
                       'peak_source': 'measured peer copy per direction (B200_PROFILING.md)'}
-    else:
+    # -- the other precision of the same workload (sub-record; the headline stays args.dtype) ----
+    other = None
+    if not args.no_extras:
+        other_dtype = 'f32' if args.dtype == 'f64' else 'f64'
+        o_steps, o_warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 3))
+        oleg = device_leg(args, other_dtype, n, gates, runtime, api, torch, dist, distributed, stream, o_steps,
+                          o_warm, True, local_rank)
+        other = {'dtype': other_dtype, 'value': oleg['value'], 'unit': UNIT, 'steps': o_steps, 'warmup': o_warm,
+                 'ms_per_step': oleg['device_ms'] / o_steps, 'roofline': oleg['roofline'],
+                 'clocks': oleg['clocks'], 'p0_check': oleg['p0'],
+                 'gpu_launches': oleg['stats']['kernel_launches']}
+    if not distributed:
         api.set_stream(0)
-    qstates.delete()
-    del qstates, proc
 
-    # -- e2e leg: public API on host objects ----------------------------------------------------
+    # -- e2e leg: the call a qgate user makes, host objects in, NumPy out -------------------------
+    # Front end: the REFERENCE's own (qgate.simulator.cuda(), unmodified, from baseline/_ref) with this
+    # package's runtime installed as qgate.simulator.cudaruntime (qgate_b200/install.py) — its
+    # per-gate Python dispatch is inside the timed region.  Without baseline/_ref: this package's
+    # mirror of that front end.
     e2e = None
     if not args.no_e2e:
-        q, ops = circuits.random_u3_cx(S, n, args.depth, seed=args.seed)
+        from baseline import reference_frontend
+        use_reference_front = reference_frontend.available() and not args.own_frontend
+        if use_reference_front:
+            import qgate_b200.install
+            qgate = reference_frontend.load()
+            front_runtime = runtime if distributed else cudaruntime
+            qgate_b200.install.install(qgate, front_runtime)
+            import qgate.script as RS
+            q, ops = circuits.random_u3_cx(RS, n, args.depth, seed=args.seed)
+
+            def make_sim():
+                return qgate.simulator.cuda(dtype=dtype, circuit_prep=qgate.prefs.one_static)
+            api_name = ('qgate.simulator.cuda().run(circuit) [reference front end, unmodified, over '
+                        'qgate_b200.install]; qubits.calc_probability; qubits.states[:4096]')
+        else:
+            q, ops = circuits.random_u3_cx(S, n, args.depth, seed=args.seed)
+
+            def make_sim():
+                prefs = {'sharding': {'exchange': args.exchange}} if distributed else {}
+                return qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static, **prefs)
+            api_name = 'qgate_b200.simulator.cuda().run(circuit); qubits.calc_probability; qubits.states[:4096]'
         e2e_steps = max(1, min(args.steps, 3))
         readback = 4096
 
@@ -425,9 +545,7 @@ def main():
 
         def e2e_step():
             t0 = time.perf_counter()
-            prefs = {'sharding': {'exchange': args.exchange}} if distributed else {}
-            sim = qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static,
-                                            **prefs)
+            sim = make_sim()
             t1 = time.perf_counter()
             sim.run(ops)                       # returns after the device has finished (synchronize)
             t2 = time.perf_counter()
@@ -436,6 +554,7 @@ def main():
             head = sim.qubits.states[:readback]
             t3 = time.perf_counter()
             sim.terminate()
+            del sim
             t4 = time.perf_counter()
             for key, dt in zip(('create_s', 'run_s', 'observe_s', 'terminate_s'),
                                (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
@@ -463,8 +582,13 @@ def main():
                'd2h_bytes_per_step': st['d2h_bytes'] // e2e_steps,
                'ms_per_step': 1e3 * e2e_s / e2e_steps, 'steps': e2e_steps,
                'split_ms': {k: 1e3 * v / e2e_steps for k, v in split.items()},
-               'api': 'qgate_b200.simulator.cuda().run(circuit); qubits.calc_probability; '
-                      'qubits.states[:4096]'}
+               'front_end': 'reference (baseline/_ref)' if use_reference_front else 'qgate_b200 mirror',
+               'api': api_name, 'p0_check': p}
+
+    # -- QFT sub-records (the metric's second half) -------------------------------------------------
+    qft = None
+    if not args.no_extras:
+        qft = qft_records(n_gpus, g_bits, args.dtype, rank)
 
     # -- CPU baseline (rank 0, N=1 only) --------------------------------------------------------
     cpu_baseline = None
@@ -493,7 +617,10 @@ def main():
                 'config': config, 'clocks': clock_info, 'e2e': e2e,
                 'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
                 'hbm_gbs_per_gpu': achieved, 'nvlink': nvlink,
-                'gates': len(gates), 'p0_check': p0}
+                'gates': len(gates), 'p0_check': p0,
+                # sub-records, not headlines: the other precision of the same workload, and the QFT
+                # half of BASELINE.json's metric
+                ('f32' if args.dtype == 'f64' else 'f64'): other, 'qft': qft}
         print(json.dumps(line))
     if distributed:
         dist.barrier()

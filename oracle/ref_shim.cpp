@@ -24,6 +24,7 @@
 #include "CPUQubitStates.h"
 #include "CPUQubitProcessor.h"
 #include "CPUQubitsStatesGetter.h"
+#include "CPUSamplingPool.h"
 
 #include <algorithm>
 #include <cmath>
@@ -567,6 +568,28 @@ int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes, const in
     std::sort(sp->empty.begin(), sp->empty.end());
     sp->finalized = true;
     *pool = reinterpret_cast<qgb_handle>(static_cast<qgate::SamplingPool *>(sp));
+    QGB_CATCH
+}
+
+/* Shim-only (not in include/qgate_b200.h; tests bind it by name): the reference's OWN pool,
+ * qgate_cpu::CPUSamplingPool<V> (CPUSamplingPool.cpp:8-63), built from a caller-supplied
+ * probability vector — what pins the engine's reference-compatible scan. */
+int qgb_ref_pool_from_prob_array(int prec, const double *prob, int n_lanes, const int *empty_lanes,
+                                 int n_empty, qgb_handle *pool) {
+    QGB_TRY
+    const size_t n = (size_t)1 << n_lanes;
+    qgate::IdList empties(empty_lanes, empty_lanes + n_empty);
+    qgate::SamplingPool *sp;
+    if (prec == QGB_PREC_FP32) {
+        float *p = static_cast<float *>(malloc(sizeof(float) * n)); /* the pool frees it */
+        for (size_t i = 0; i < n; ++i) p[i] = (float)prob[i];
+        sp = new qgate_cpu::CPUSamplingPool<float>(p, n_lanes, empties);
+    } else {
+        double *p = static_cast<double *>(malloc(sizeof(double) * n));
+        for (size_t i = 0; i < n; ++i) p[i] = prob[i];
+        sp = new qgate_cpu::CPUSamplingPool<double>(p, n_lanes, empties);
+    }
+    *pool = reinterpret_cast<qgb_handle>(sp);
     QGB_CATCH
 }
 

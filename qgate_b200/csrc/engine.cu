@@ -192,6 +192,9 @@ struct Pool {
     int n_lanes;
     double *d_cum = nullptr;
     double *d_sums = nullptr; /* block sums + total, kept between `partial` and `finalize` */
+    const void *src_amp = nullptr; /* pool over all lanes of one state vector in index order: the scan */
+                                   /* reads |a|^2 straight from the amplitudes (not owned; the state    */
+                                   /* must not change between `partial` and `finalize`)                 */
     bool finalized = false;
     SortedBits empty;
 };
@@ -231,6 +234,7 @@ struct Options {
      * (CPUSamplingPool.cpp:13-47, CPUQubitsStatesGetter.cpp:179-247) — so that sampled indices are
      * bit-identical to its for identical probabilities.  0: the parallel float64 scan. */
     int64_t pool_compat_workers = 0;
+    int64_t pool_from_amplitudes = 1; /* 0: always materialise the probability vector first (A/B switch) */
 };
 
 struct Engine {
@@ -559,11 +563,29 @@ int qgb_devices_initialize(const int *device_ids, int n_device_ids, int max_po2i
     int n = 0;
     CUDA_CHECK(cudaGetDeviceCount(&n));
     if (n == 0) fail(QGB_ERR_CUDA, "no CUDA device.");
+    /* device_ids (cudaruntime.set_preference, qgate/simulator/cudaruntime.py:33-41).  This engine
+     * drives ONE GPU per process (N GPUs = N ranks under torchrun, qgate_b200/dist.py), so:
+     *   []               the current device;
+     *   [d]              device d;
+     *   [d, d, ..., d]   the reference's "logical devices on one GPU" (tests/test_multidevice.py:
+     *                    13-21, examples/mgpu.py:10-16): k logical devices with a budget of
+     *                    memory_store_size each are one device with k times that budget — one
+     *                    allocation per state vector, chunking is never needed;
+     *   distinct ids     refused: silently using the first one would give the caller one GPU's
+     *                    memory where it asked for several. */
     int dev = 0;
-    if (n_device_ids > 0)
-        dev = device_ids[0]; /* one process drives one GPU; further ids are other ranks' shards */
-    else
+    if (n_device_ids > 0) {
+        dev = device_ids[0];
+        for (int i = 1; i < n_device_ids; ++i)
+            if (device_ids[i] != dev)
+                fail(QGB_ERR_INVALID,
+                     "device_ids names %d different GPUs: this runtime drives one GPU per process; launch one "
+                     "process per GPU (torchrun --nproc-per-node N) and the state vector is sharded over the "
+                     "ranks (qgate_b200.dist).", n_device_ids);
+        if (memory_store_size >= 0) memory_store_size *= n_device_ids;
+    } else {
         CUDA_CHECK(cudaGetDevice(&dev));
+    }
     if (dev < 0 || dev >= n) fail(QGB_ERR_INVALID, "device id %d out of range [0, %d).", dev, n);
     CUDA_CHECK(cudaSetDevice(dev));
     g.device = dev;
@@ -1164,6 +1186,25 @@ int qgb_getter_prepare_prob_array(qgb_handle getter, void *prob, const int *lane
     QGB_CATCH
 }
 
+/* Fills the pool's source: the marginal probability vector in d_cum, or — one state vector, every
+ * lane in the pool, index order, default (float64) scan — just a pointer to the amplitudes. */
+static void pool_set_source(Pool *p, int prec, const int *lane_tables, const int *n_per, const qgb_handle *list,
+                            int n_qstates, int n_lanes, int n_hidden) {
+    if (n_qstates == 1 && n_hidden == 0 && g.opt.pool_compat_workers <= 0 && g.opt.pool_from_amplitudes) {
+        QStates *qs = QS(list[0]);
+        check_allocated(qs);
+        bool identity = qs->prec == prec && qs->n_lanes == n_lanes && n_per[0] == n_lanes;
+        for (int l = 0; identity && l < n_lanes; ++l) identity = lane_tables[l] == l;
+        if (identity) {
+            flush(qs);
+            p->d_cum = static_cast<double *>(g.pool.alloc(sizeof(double) << n_lanes));
+            p->src_amp = qs->d_amp;
+            return;
+        }
+    }
+    p->d_cum = device_prob_array(prec, lane_tables, n_per, list, n_qstates, n_lanes, n_hidden);
+}
+
 /* scan phases 1+2 over d_prob (2^n_lanes doubles): leaves the block sums in pool->d_sums and
  * returns the total (host value) */
 static double pool_scan_partial(Pool *p) {
@@ -1171,7 +1212,7 @@ static double pool_scan_partial(Pool *p) {
     const int64_t n_blocks = (n + 4095) / 4096;
     p->d_sums = static_cast<double *>(g.pool.alloc(sizeof(double) * (size_t)(n_blocks + 1)));
     double *d_total = p->d_sums + n_blocks;
-    CUDA_CHECK(launch_scan_phase1(p->d_cum, n, p->d_sums, g.stream));
+    CUDA_CHECK(launch_scan_phase1(p->prec, p->src_amp, p->d_cum, n, p->d_sums, g.stream));
     CUDA_CHECK(launch_scan_phase2(p->d_sums, n_blocks, d_total, g.stream));
     CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, d_total, sizeof(double), cudaMemcpyDeviceToHost, g.stream));
     stream_sync();
@@ -1184,7 +1225,8 @@ static double pool_scan_partial(Pool *p) {
 static void pool_scan_finalize(Pool *p, double offset, double total) {
     if (p->finalized || !p->d_sums) fail(QGB_ERR_RUNTIME, "sampling pool is already finalized.");
     const int64_t n = (int64_t)1 << p->n_lanes;
-    CUDA_CHECK(launch_scan_phase3(p->d_cum, n, p->d_sums, offset, 1. / total, g.stream));
+    CUDA_CHECK(launch_scan_phase3(p->prec, p->src_amp, p->d_cum, n, p->d_sums, offset, 1. / total, g.stream));
+    p->src_amp = nullptr;
     g.stats.kernel_launches += 1;
     g.pool.release(p->d_sums); /* stream-ordered: reused only by later work on the same stream */
     p->d_sums = nullptr;
@@ -1287,7 +1329,7 @@ int qgb_getter_create_sampling_pool(qgb_handle getter, const int *lane_tables, c
     p->empty.n = 0;
     g.pools.insert(p);
     try {
-        p->d_cum = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
+        pool_set_source(p, gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
         pool_set_empty_lanes(p, empty_lanes, n_empty);
     } catch (...) {
         pool_destroy(p);
@@ -1310,7 +1352,7 @@ int qgb_getter_create_sampling_pool_partial(qgb_handle getter, const int *lane_t
     p->empty.n = 0;
     g.pools.insert(p);
     try {
-        p->d_cum = device_prob_array(gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
+        pool_set_source(p, gt->prec, lane_tables, n_per, qstates_list, n_qstates, n_lanes, n_hidden);
     } catch (...) {
         pool_destroy(p);
         throw;
@@ -1430,6 +1472,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "reg_bits_fp64") g.opt.reg_bits_fp64 = value;
     else if (k == "warp_local") g.opt.warp_local = value;
     else if (k == "pool_compat_workers") g.opt.pool_compat_workers = value;
+    else if (k == "pool_from_amplitudes") g.opt.pool_from_amplitudes = value;
     else if (k == "tma_ws") tma_pass_set_warp_specialised((int)value);
     else fail(QGB_ERR_INVALID, "unknown option '%s'.", k.c_str());
     QGB_CATCH

@@ -104,12 +104,15 @@ cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, i
                                     cudaStream_t stream);
 
 /* ---- sampling pool ------------------------------------------------------------------- */
-/* in-place inclusive scan of d_prob[0..n) in double with a fixed tiling (deterministic);
- * d_block_sums holds ceil(n / 4096) doubles; *d_total receives the grand total. */
-cudaError_t launch_scan_phase1(const double *d_prob, int64_t n, double *d_block_sums, cudaStream_t stream);
+/* inclusive scan in double with a fixed tiling (deterministic) of either d_prob[0..n) in place
+ * (amp == nullptr) or of |amp[i]|^2 computed on the fly (amp = 2^n_lanes amplitudes of precision
+ * `prec`; the probability vector is then never materialised).  d_block_sums holds ceil(n / 4096)
+ * doubles; *d_total receives the grand total. */
+cudaError_t launch_scan_phase1(int prec, const void *amp, const double *d_prob, int64_t n, double *d_block_sums,
+                               cudaStream_t stream);
 cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d_total, cudaStream_t stream);
 /* cum[i] = (global_offset + offset_block + inclusive_scan_in_block) * norm */
-cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums,
+cudaError_t launch_scan_phase3(int prec, const void *amp, double *d_cum, int64_t n, const double *d_block_sums,
                                double global_offset, double norm, cudaStream_t stream);
 /* obs[i] = deposit(upper_bound(cum, r_i), perm); r is cast to float first when prec is FP32
  * (CPUSamplingPool.cpp:74) */

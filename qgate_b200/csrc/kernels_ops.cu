@@ -364,52 +364,102 @@ cast_from_double_kernel(real *__restrict__ out, const double *__restrict__ in, i
         out[j] = (real)in[j];
 }
 
-/* ---- sampling pool: inclusive scan (CPUSamplingPool.cpp:8-63) ------------------------------ */
+/* ---- sampling pool: inclusive scan (CPUSamplingPool.cpp:8-63) ------------------------------
+ * Three phases over blocks of 4096 entries, all sums in double with a FIXED combination tree
+ * (deterministic): (1) block sums, (2) exclusive scan of the block sums + grand total, (3) the
+ * inclusive scan inside every block, + block offset, x 1 / total (the reference's order: scan, then
+ * multiply, CPUSamplingPool.cpp:36).  Phases 1 and 3 share block_scan, so a block's total is the
+ * same number in both and the cumulative array is monotonic across block boundaries.
+ *
+ * The source of phases 1 and 3 is either the marginal probability vector (doubles) or — pools over
+ * ALL lanes of one state vector in index order, the 30-qubit Grover case — the amplitudes
+ * themselves: |a|^2 is recomputed in both phases and the 2^n-entry probability vector is never
+ * written (40 instead of 56 bytes of HBM traffic per complex128 amplitude).
+ *
+ * Memory access: a block moves its 4096 entries with coalesced loads through shared memory (entry
+ * i at slot i + i / 16: the 16 consecutive entries of a thread then lie in distinct banks). */
 #define SCAN_THREADS 256
 #define SCAN_PER_THREAD 16
 #define SCAN_BLOCK (SCAN_THREADS * SCAN_PER_THREAD)
+#define SCAN_SLOT(i) ((i) + ((i) >> 4))
+#define SCAN_SMEM (SCAN_BLOCK + SCAN_BLOCK / 16)
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase1_kernel(const double *__restrict__ prob, int64_t n, double *__restrict__ block_sums) {
-    const int64_t begin = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
-    double acc = 0.;
+struct SrcProb {
+    const double *p;
+    __device__ __forceinline__ double at(int64_t i) const { return p[i]; }
+};
+template <typename real> struct SrcAmp {
+    const typename Cplx<real>::type *a;
+    /* the value prob_array_kernel stores for one qstates without hidden lanes */
+    __device__ __forceinline__ double at(int64_t i) const { return (double)abs2_exact(a[i]); }
+};
+
+/* exclusive prefix of `v` over the block in thread order + the block total; the same shuffle tree
+ * whatever the data (fixed order of additions).  `part` holds 8 doubles of shared memory. */
+__device__ __forceinline__ double block_scan(double v, double *part, double &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double incl = v;
 #pragma unroll
-    for (int u = 0; u < SCAN_PER_THREAD; ++u)
-        if (begin + u < n) acc += prob[begin + u];
-    /* same combination tree as phase 3 uses for the thread offsets */
-    __shared__ double tsum[SCAN_THREADS];
-    tsum[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.;
-        for (int t = 0; t < SCAN_THREADS; ++t) s += tsum[t];
-        block_sums[blockIdx.x] = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
+    __syncthreads(); /* protect `part` from a previous use */
+    if (lane == 31) part[w] = incl;
+    __syncthreads();
+    double before = 0., all = 0.;
+#pragma unroll
+    for (int k = 0; k < SCAN_THREADS / 32; ++k) {
+        const double pk = part[k];
+        if (k < w) before += pk;
+        all += pk;
+    }
+    total = all;
+    return before + (incl - v);
 }
 
-/* exclusive scan of the block sums in place (sequential per thread chunk + sequential over
+/* the block's entries -> shared memory (coalesced), then this thread's 16 consecutive ones */
+template <typename SRC>
+__device__ __forceinline__ void scan_load(const SRC &src, int64_t n, double *stage, double (&v)[SCAN_PER_THREAD]) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) {
+        const int i = u * SCAN_THREADS + (int)threadIdx.x;
+        stage[SCAN_SLOT(i)] = base + i < n ? src.at(base + i) : 0.;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) v[u] = stage[SCAN_SLOT((int)threadIdx.x * SCAN_PER_THREAD + u)];
+}
+
+template <typename SRC>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_phase1_kernel(const SRC src, int64_t n, double *__restrict__ block_sums) {
+    __shared__ double stage[SCAN_SMEM];
+    __shared__ double part[SCAN_THREADS / 32];
+    double v[SCAN_PER_THREAD];
+    scan_load(src, n, stage, v);
+    double acc = 0.;
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) acc += v[u];
+    double total;
+    block_scan(acc, part, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+/* exclusive scan of the block sums in place (sequential per thread chunk, block_scan over the
  * chunk totals: deterministic), grand total to *total */
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SCAN_THREADS)
 scan_phase2_kernel(double *__restrict__ block_sums, int64_t n_blocks, double *__restrict__ total) {
-    __shared__ double chunk_sum[1024];
+    __shared__ double part[SCAN_THREADS / 32];
     const int64_t per = (n_blocks + blockDim.x - 1) / blockDim.x;
     const int64_t begin = (int64_t)threadIdx.x * per;
     const int64_t end = begin + per < n_blocks ? begin + per : n_blocks;
     double acc = 0.;
     for (int64_t i = begin; i < end; ++i) acc += block_sums[i];
-    chunk_sum[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.;
-        for (int t = 0; t < (int)blockDim.x; ++t) {
-            const double c = chunk_sum[t];
-            chunk_sum[t] = s;
-            s += c;
-        }
-        *total = s;
-    }
-    __syncthreads();
-    acc = chunk_sum[threadIdx.x];
+    double all;
+    acc = block_scan(acc, part, all);
+    if (threadIdx.x == 0) *total = all;
     for (int64_t i = begin; i < end; ++i) {
         const double c = block_sums[i];
         block_sums[i] = acc;
@@ -417,35 +467,36 @@ scan_phase2_kernel(double *__restrict__ block_sums, int64_t n_blocks, double *__
     }
 }
 
+template <typename SRC>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_phase3_kernel(double *__restrict__ prob, int64_t n, const double *__restrict__ block_sums,
+scan_phase3_kernel(const SRC src, double *__restrict__ cum, int64_t n, const double *__restrict__ block_sums,
                    double global_offset, double norm) {
-    const int64_t begin = (int64_t)blockIdx.x * SCAN_BLOCK + (int64_t)threadIdx.x * SCAN_PER_THREAD;
+    __shared__ double stage[SCAN_SMEM];
+    __shared__ double part[SCAN_THREADS / 32];
     double v[SCAN_PER_THREAD];
+    scan_load(src, n, stage, v);
     double acc = 0.;
 #pragma unroll
     for (int u = 0; u < SCAN_PER_THREAD; ++u) {
-        acc += (begin + u < n) ? prob[begin + u] : 0.;
+        acc += v[u];
         v[u] = acc;
     }
-    __shared__ double tsum[SCAN_THREADS];
-    tsum[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.;
-        for (int t = 0; t < SCAN_THREADS; ++t) {
-            const double c = tsum[t];
-            tsum[t] = s;
-            s += c;
-        }
-    }
-    __syncthreads();
+    double total;
+    const double before = block_scan(acc, part, total);
     /* global_offset: total of the lower ranks' shards (0 on one GPU, which keeps the sum exact);
      * norm = 1 / sum, then cum *= norm (CPUSamplingPool.cpp:36) */
-    const double offset = global_offset + (block_sums[blockIdx.x] + tsum[threadIdx.x]);
+    const double offset = global_offset + (block_sums[blockIdx.x] + before);
+    __syncthreads(); /* every thread has read its entries: the staging area carries the results out */
 #pragma unroll
     for (int u = 0; u < SCAN_PER_THREAD; ++u)
-        if (begin + u < n) prob[begin + u] = (offset + v[u]) * norm;
+        stage[SCAN_SLOT((int)threadIdx.x * SCAN_PER_THREAD + u)] = (offset + v[u]) * norm;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SCAN_BLOCK;
+#pragma unroll
+    for (int u = 0; u < SCAN_PER_THREAD; ++u) {
+        const int i = u * SCAN_THREADS + (int)threadIdx.x;
+        if (base + i < n) cum[base + i] = stage[SCAN_SLOT(i)];
+    }
 }
 
 /* ---- sampling pool: upper_bound search + empty-lane deposit (CPUSamplingPool.cpp:71-81) ---- */
@@ -687,21 +738,38 @@ cudaError_t launch_cast_from_double(int prec, void *d_out, const double *d_in, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_phase1(const double *d_prob, int64_t n, double *d_block_sums, cudaStream_t stream) {
+/* amp == nullptr: the source is d_cum itself (the marginal probability vector, scanned in place) */
+cudaError_t launch_scan_phase1(int prec, const void *amp, const double *d_prob, int64_t n, double *d_block_sums,
+                               cudaStream_t stream) {
     const unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    scan_phase1_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums);
+    if (!amp)
+        scan_phase1_kernel<SrcProb><<<nblocks, SCAN_THREADS, 0, stream>>>(SrcProb{d_prob}, n, d_block_sums);
+    else if (prec == 1)
+        scan_phase1_kernel<SrcAmp<double>><<<nblocks, SCAN_THREADS, 0, stream>>>(
+            SrcAmp<double>{reinterpret_cast<const double2 *>(amp)}, n, d_block_sums);
+    else
+        scan_phase1_kernel<SrcAmp<float>><<<nblocks, SCAN_THREADS, 0, stream>>>(
+            SrcAmp<float>{reinterpret_cast<const float2 *>(amp)}, n, d_block_sums);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan_phase2(double *d_block_sums, int64_t n_blocks, double *d_total, cudaStream_t stream) {
-    scan_phase2_kernel<<<1, 1024, 0, stream>>>(d_block_sums, n_blocks, d_total);
+    scan_phase2_kernel<<<1, SCAN_THREADS, 0, stream>>>(d_block_sums, n_blocks, d_total);
     return cudaGetLastError();
 }
 
-cudaError_t launch_scan_phase3(double *d_prob, int64_t n, const double *d_block_sums, double global_offset,
-                               double norm, cudaStream_t stream) {
+cudaError_t launch_scan_phase3(int prec, const void *amp, double *d_cum, int64_t n, const double *d_block_sums,
+                               double global_offset, double norm, cudaStream_t stream) {
     const unsigned nblocks = (unsigned)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
-    scan_phase3_kernel<<<nblocks, SCAN_THREADS, 0, stream>>>(d_prob, n, d_block_sums, global_offset, norm);
+    if (!amp)
+        scan_phase3_kernel<SrcProb><<<nblocks, SCAN_THREADS, 0, stream>>>(SrcProb{d_cum}, d_cum, n, d_block_sums,
+                                                                         global_offset, norm);
+    else if (prec == 1)
+        scan_phase3_kernel<SrcAmp<double>><<<nblocks, SCAN_THREADS, 0, stream>>>(
+            SrcAmp<double>{reinterpret_cast<const double2 *>(amp)}, d_cum, n, d_block_sums, global_offset, norm);
+    else
+        scan_phase3_kernel<SrcAmp<float>><<<nblocks, SCAN_THREADS, 0, stream>>>(
+            SrcAmp<float>{reinterpret_cast<const float2 *>(amp)}, d_cum, n, d_block_sums, global_offset, norm);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,12 @@ import sys
 import pytest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# Pin the worker count of the reference CPU runtime (oracle/_ref reads QGATE_NUM_WORKERS once, at its
+# first parallel loop: Parallel.cpp:21-38).  Its sampling pool scans one span per worker, so the
+# count is part of what "the reference's sampled indices" means; tests that ask the engine for the
+# reference-compatible pool (option pool_compat_workers) pass the same number.
+os.environ.setdefault('QGATE_NUM_WORKERS', str(min(16, len(os.sched_getaffinity(0)))))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 

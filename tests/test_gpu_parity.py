@@ -7,6 +7,7 @@ Tolerances are BASELINE.json's: amplitudes within 1e-12 (complex128) / 1e-5 (com
 relative to max|a|; measurement outcomes and complex128 sampled indices bit-exact for
 identical random draws."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -64,7 +65,7 @@ def test_measure_all_bits_exact(golden, cuda_runtime, name, prep, rt, dtype):
     sim.qubits.set_ordering(q)
     key = 'measure/{}/{}/{}'.format(name, prep, rt)
     assert np.array_equal(np.array(sim.values.get(refs), np.int64), golden[key + '/bits'])
-    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype] * 10
+    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype]
 
 
 @pytest.mark.parametrize('prep', PREPS)
@@ -77,7 +78,7 @@ def test_midcircuit_measure_reset_if(golden, cuda_runtime, prep, rt, dtype):
     sim.qubits.set_ordering(q)
     key = 'measure/midcircuit/{}/{}'.format(prep, rt)
     assert np.array_equal(np.array(sim.values.get(refs), np.int64), golden[key + '/bits'])
-    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype] * 10
+    assert cases.rel_err(sim.qubits.states[:], golden[key + '/states']) < cases.TOL[dtype]
 
 
 class Probe:
@@ -424,3 +425,245 @@ def test_simulator_sample_shot_for_shot(cuda_runtime, ref_runtime, dtype):
         sim.terminate()
     assert np.array_equal(outs[0], outs[1])
     assert len(set(outs[0].tolist())) > 3
+
+
+# ---- exact mode: bit-identical to the reference CPU runtime -------------------------------------
+
+REF_WORKERS = int(os.environ['QGATE_NUM_WORKERS'])   # pinned in tests/conftest.py
+
+
+@pytest.fixture
+def exact_mode(cuda_runtime):
+    """Option exact = 1 (every gate as submitted, in the reference's arithmetic operation by
+    operation) + pool_compat_workers = the reference's worker count (its scan, span for span)."""
+    api = cuda_runtime.get_api()
+    api.set_option('exact', 1)
+    api.set_option('pool_compat_workers', REF_WORKERS)
+    yield api
+    api.set_option('exact', 0)
+    api.set_option('pool_compat_workers', 0)
+
+
+@pytest.mark.parametrize('prep', PREPS)
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_exact_mode_is_bit_identical_to_the_reference(cuda_runtime, ref_runtime, exact_mode, dtype, prep):
+    """18 qubits (2^18 pool entries: the reference scans W spans, Parallel.cpp:60-67): amplitudes,
+    marginal probabilities and 200 000 sampled indices EQUAL to the reference CPU runtime's, bit for
+    bit, in both precisions — sampled indices bit-exact given the same uniform draws."""
+    q, ops = circuits.random_u3_cx(S, 18, 5, seed=41)
+    q2, ops2 = circuits.mixed_gate_zoo(S, 18, 150, seed=17, qregs=q)
+    ops = ops + ops2
+    rnd = np.random.RandomState(12).random_sample(200000)
+    outs = []
+    for rt in (cuda_runtime, ref_runtime.module):
+        sim = cases.make_sim(rt, dtype, prep)
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        states = sim.qubits.states[:]
+        full = sim.qubits.create_sampling_pool(q).sample(len(rnd), rnd).intarray
+        hidden_order = q[1::2] + q[0:6:2]                       # 12 pool lanes, 6 hidden lanes
+        hidden = sim.qubits.create_sampling_pool(hidden_order).sample(len(rnd), rnd).intarray
+        prob_hidden = sim.qubits.create_sampling_pool(hidden_order, Probe).prob
+        prob_full = sim.qubits.create_sampling_pool(q, Probe).prob
+        outs.append((states, full, hidden, prob_hidden, prob_full))
+        sim.terminate()
+    for got, want, what in zip(outs[0], outs[1], ('amplitudes', 'indices', 'indices with hidden lanes',
+                                                  'marginal probabilities', 'probabilities')):
+        assert got.dtype == want.dtype, what
+        assert np.array_equal(got, want), (what, np.dtype(dtype).name, prep, int(np.sum(got != want)))
+    assert len(np.unique(outs[0][1])) > 1000
+
+
+@pytest.mark.parametrize('name', ('rand10x20', 'zoo9', 'grover8'))
+@pytest.mark.parametrize('prep', PREPS)
+def test_complex64_sampling_pool_indices_exact_in_exact_mode(golden, cuda_runtime, exact_mode, name, prep):
+    """The golden complex64 sampled indices (recorded from the real reference), which the default
+    float64 pool matches to 99.5 %, are reproduced EXACTLY by the reference-compatible pool."""
+    rnd = np.random.RandomState(7).random_sample(20000)
+    sim = cases.make_sim(cuda_runtime, np.float32, prep)
+    q, ops = cases.CIRCUITS[name]()
+    empty = S.new_qregs(2)
+    sim.run(ops)
+    key = 'sampling/{}/{}/cpu32'.format(name, prep)
+    orderings = {'full': q, 'hidden': q[1::2],
+                 'empty': [q[3], empty[0], q[0], q[5], empty[1], q[1]],
+                 'reversed': list(reversed(q))}
+    for tag, ordering in orderings.items():
+        got = sim.qubits.create_sampling_pool(ordering).sample(20000, rnd).intarray
+        assert np.array_equal(got, golden[key + '/' + tag]), tag
+    # (the golden marginal vector itself is not compared bit for bit: WHICH hidden lane lands on which
+    # low bit follows python set iteration over qreg ids in the front end, qubits_handler.py:45-56, so
+    # the golden run summed the same 32 values in another order; the live comparison, same front end
+    # on both runtimes, is test_exact_mode_is_bit_identical_to_the_reference)
+    prob = sim.qubits.create_sampling_pool(q[1::2], Probe).prob
+    assert np.allclose(prob, golden[key + '/prob_hidden'], rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+@pytest.mark.parametrize('n_lanes', (10, 17, 21))
+def test_compatible_pool_from_the_reference_probabilities(cuda_runtime, ref_runtime, dtype, n_lanes):
+    """The scan alone: the engine's reference-compatible pool and the reference's pool, built from
+    the SAME probability vector, answer 300 000 draws identically (1 span below 2^16 entries,
+    W spans above)."""
+    import ctypes as C
+    rng = np.random.RandomState(n_lanes)
+    prob = rng.random_sample(1 << n_lanes) ** 6          # peaked: spans with very different totals
+    prob = (prob / prob.sum()).astype(dtype)
+    rnd = rng.random_sample(300000)
+    outs = []
+    for api, workers in ((cuda_runtime.get_api(), REF_WORKERS), (ref_runtime.module.api, 0)):
+        if not ref_runtime.module.initialized:
+            ref_runtime.module.module_init()
+        if not cuda_runtime.initialized:
+            cuda_runtime.module_init()
+        api.set_option('pool_compat_workers', workers)
+        pool = C.c_uint64(0)
+        p64 = np.ascontiguousarray(prob, np.float64)
+        # the engine's public entry point / the shim-only constructor of the reference's own
+        # qgate_cpu::CPUSamplingPool (oracle/ref_shim.cpp)
+        fn = api.lib.qgb_pool_from_prob_array if workers else api.lib.qgb_ref_pool_from_prob_array
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_int), C.c_int,
+                       C.POINTER(C.c_uint64)]
+        api.check(fn(1 if dtype is np.float64 else 2, p64.ctypes.data_as(C.POINTER(C.c_double)), n_lanes,
+                     api.int_array([]), 0, C.byref(pool)))
+        obs = np.empty(len(rnd), np.int64)
+        api.call('qgb_pool_sample', pool.value, obs.ctypes.data_as(C.POINTER(C.c_int64)), len(rnd),
+                 rnd.ctypes.data_as(C.POINTER(C.c_double)))
+        api.call('qgb_pool_delete', pool.value)
+        api.set_option('pool_compat_workers', 0)
+        outs.append(obs)
+    assert np.array_equal(outs[0], outs[1]), int(np.sum(outs[0] != outs[1]))
+
+
+# ---- the reference CPU runtime at the survey's sizes (SURVEY.md section 8d) ----------------------
+
+def _compare_in_chunks(sim_a, sim_b, n, chunk_lanes=24):
+    """max |a - b| and max |b| over the full state vectors, read 2^chunk_lanes amplitudes at a time"""
+    err = scale = 0.
+    step = 1 << min(n, chunk_lanes)
+    for begin in range(0, 1 << n, step):
+        a = sim_a.qubits.states[begin:begin + step]
+        b = sim_b.qubits.states[begin:begin + step]
+        err = max(err, float(np.abs(a - b).max()))
+        scale = max(scale, float(np.abs(b).max()))
+    return err, scale
+
+
+def test_random_circuit_24_qubits_depth_200_against_reference(cuda_runtime, ref_runtime):
+    """BASELINE configs[1]'s generator at 24 qubits, FULL depth (200 layers, 7 100 gates): dense
+    gates on every lane, high lanes included, through the default fused passes, in both precisions,
+    against the reference CPU runtime."""
+    n = 24
+    q, ops = circuits.random_u3_cx(S, n, 200, seed=1234)
+    ref64 = cases.make_sim(ref_runtime.module, np.float64, 'one_static')
+    ref64.run(ops)
+    ref64.qubits.set_ordering(q)
+    ref32 = cases.make_sim(ref_runtime.module, np.float32, 'one_static')
+    ref32.run(ops)
+    ref32.qubits.set_ordering(q)
+    api = cuda_runtime.get_api()
+    for dtype in (np.float64, np.float32):
+        api.stats_reset()
+        sim = cases.make_sim(cuda_runtime, dtype, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        stats = api.stats()
+        assert stats['shear_ops'] > 1000 and stats['tile_passes'] > 100, stats
+        err, scale = _compare_in_chunks(sim, ref64, n)
+        assert err / scale < cases.TOL[dtype], (np.dtype(dtype).name, err / scale)
+        if dtype is np.float32:
+            err, scale = _compare_in_chunks(sim, ref32, n)
+            assert err / scale < cases.TOL[dtype], ('vs complex64 reference', err / scale)
+        p_gpu = [sim.qubits.calc_probability(qr) for qr in (q[0], q[11], q[23])]
+        p_ref = [ref64.qubits.calc_probability(qr) for qr in (q[0], q[11], q[23])]
+        assert np.abs(np.array(p_gpu) - np.array(p_ref)).max() < (1e-12 if dtype is np.float64 else 1e-5)
+        sim.terminate()
+    ref64.terminate()
+    ref32.terminate()
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_random_circuit_28_qubits_depth_4_against_reference(cuda_runtime, ref_runtime, dtype):
+    """The same generator at 28 qubits (4 / 2 GiB state), 4 layers: tile lanes, tensor-map groups
+    and outside-tile predicates at a BASELINE-size lane count."""
+    n = 28
+    q, ops = circuits.random_u3_cx(S, n, 4, seed=1234)
+    ref = cases.make_sim(ref_runtime.module, dtype, 'one_static')
+    ref.run(ops)
+    ref.qubits.set_ordering(q)
+    sim = cases.make_sim(cuda_runtime, dtype, 'one_static')
+    sim.run(ops)
+    sim.qubits.set_ordering(q)
+    err, scale = _compare_in_chunks(sim, ref, n)
+    assert err / scale < cases.TOL[dtype], err / scale
+    sim.terminate()
+    ref.terminate()
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_grover_22_qubits_against_reference(cuda_runtime, ref_runtime, dtype):
+    """BASELINE configs[2] at 22 qubits: 8 Grover iterations (21-fold controlled Z), 1M shots from
+    the sampling pool, then every qubit measured.
+
+    The distribution is FLAT (4M bins of 2.4e-7, one of 6.9e-5): which bin a draw falls into then
+    depends on the rounding of a 4M-term running sum — the reference's own pool and a NumPy cumsum
+    of the reference's own probabilities already disagree on ~90 of 1M draws (measured), a float32
+    pool on a quarter of them.  So: default (fused passes, parallel float64 scan) = amplitudes within
+    tolerance, outcomes identical, indices agreeing up to that sensitivity; exact mode (reference
+    arithmetic + reference scan) = every one of the 1M indices identical, both precisions."""
+    n = 22
+    api = cuda_runtime.get_api()
+    q, ops = circuits.grover(S, n, 8, 0x2AAAAA & ((1 << n) - 1))
+    refs = S.new_references(n)
+    rnd = np.random.RandomState(7).random_sample(1000000)
+    outs = []
+    for rt, exact in ((cuda_runtime, 0), (cuda_runtime, 1), (ref_runtime.module, 0)):
+        api.set_option('exact', exact)
+        api.set_option('pool_compat_workers', REF_WORKERS if exact else 0)
+        sim = cases.make_sim(rt, dtype, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        states = sim.qubits.states[:]
+        samples = sim.qubits.create_sampling_pool(q).sample(len(rnd), rnd).intarray
+        np.random.seed(11)
+        sim.run([S.measure(r, qr) for r, qr in zip(refs, q)])
+        outs.append((states, samples, sim.values.get(refs)))
+        sim.terminate()
+    api.set_option('exact', 0)
+    api.set_option('pool_compat_workers', 0)
+    (a, s_a, bits_a), (x, s_x, bits_x), (b, s_b, bits_b) = outs
+    assert cases.rel_err(a, b) < cases.TOL[dtype]
+    assert bits_a == bits_b and bits_x == bits_b
+    assert np.array_equal(x, b)
+    assert np.array_equal(s_x, s_b)
+    assert np.mean(s_a == s_b) > (0.9995 if dtype is np.float64 else 0.7)
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_phase_estimation_20_bits_against_reference(cuda_runtime, ref_runtime, dtype):
+    """BASELINE configs[3] at 20 + 1 qubits: amplitudes, then 1M shots from a pool over the counting
+    bits (the target is a hidden lane).  The inverse QFT has no final swaps, so the register reads
+    the estimate bit-reversed (examples/phase_estimation.py:36-42): the histogram peaks at
+    reverse_20(round(0.1 * 2^20))."""
+    n_bits = 20
+    bits, target, ops = circuits.phase_estimation(S, n_bits, 0.1)
+    rnd = np.random.RandomState(3).random_sample(1000000)
+    outs = []
+    for rt in (cuda_runtime, ref_runtime.module):
+        sim = cases.make_sim(rt, dtype, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(bits + [target])
+        states = sim.qubits.states[:]
+        samples = sim.qubits.create_sampling_pool(bits).sample(len(rnd), rnd).intarray
+        outs.append((states, samples))
+        sim.terminate()
+    (a, s_a), (b, s_b) = outs
+    assert cases.rel_err(a, b) < cases.TOL[dtype]
+    natural = int(round(0.1 * (1 << n_bits)))
+    want_peak = int(format(natural, '0{}b'.format(n_bits))[::-1], 2)
+    assert int(np.bincount(s_a).argmax()) == want_peak == int(np.bincount(s_b).argmax())
+    if dtype is np.float64:
+        assert np.array_equal(s_a, s_b)
+    else:
+        assert np.mean(s_a == s_b) > 0.995

@@ -1,12 +1,12 @@
-"""CPU suite, part 4 (build container only): the drop-in claim at the Python boundary.
+"""The drop-in claim at the Python boundary.
 
-The REAL reference package is imported from a scratch copy of /root/reference (recipe of
-tests/golden/make_golden.py), this package's runtime objects (qgate_b200/native.py) are installed
+The REAL reference package is imported (baseline/reference_frontend.py: a scratch build of
+/root/reference in the build container, baseline/_ref on the GPU box), this package's runtime objects (qgate_b200/native.py) are installed
 as `qgate.simulator.cudaruntime` (qgate_b200/install.py), and the reference's OWN unittest
 modules are run: their `...CUDA` classes then execute the reference's unmodified front end
 (Simulator, ModelExecutor, RopExecutor, QubitsHandler, Qubits) on top of our wrappers and the C ABI.
-Here the library behind the ABI is the reference-CPU shim (no GPU in this container); on a GPU box
-the same wrappers sit on libqgate_b200.so.  Skipped where /root/reference is absent."""
+The library behind the ABI is the reference-CPU shim in the CPU suite and libqgate_b200.so in the
+`-m gpu` suite (test_reference_suite_on_the_cuda_library)."""
 import os
 import sys
 import types
@@ -15,9 +15,12 @@ import unittest
 import numpy as np
 import pytest
 
-REFERENCE = '/root/reference'
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, 'tests')),
-                                reason='/root/reference is not present (GPU box)')
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+from baseline import reference_frontend  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not reference_frontend.available(),
+                                reason='the reference package is neither under baseline/_ref nor at /root/reference')
 
 MODULES = ['test_unary_gate', 'test_control_gate', 'test_calc_prob', 'test_measure', 'test_reset',
            'test_if', 'test_get_states', 'test_join', 'test_sampling_pool', 'test_swap_gate',
@@ -28,31 +31,40 @@ MODULES = ['test_unary_gate', 'test_control_gate', 'test_calc_prob', 'test_measu
 
 
 @pytest.fixture(scope='module')
-def reference_with_our_runtime():
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
-    import make_golden
-    qgate = make_golden.import_reference()
-    from oracle import ref_runtime
-    if not ref_runtime.available():
-        ref_runtime.build()
-    import qgate_b200.install
-    qgate_b200.install.install(qgate, ref_runtime.module)
-    if not hasattr(np, 'int'):
-        np.int = int                  # the reference tests use the removed alias
+def reference_package():
+    qgate = reference_frontend.load()
     pkg = types.ModuleType('tests')   # skip tests/__init__.py (it star-imports the PLY parser tests)
-    pkg.__path__ = [os.path.join(make_golden.SCRATCH, 'tests')]
+    pkg.__path__ = [os.path.join(reference_frontend.root(), 'tests')]
     saved = sys.modules.get('tests')
     sys.modules['tests'] = pkg
     yield qgate
     if saved is not None:
         sys.modules['tests'] = saved
     for name in [n for n in sys.modules if n.startswith('tests.test_')]:
-        if getattr(sys.modules[name], '__file__', '').startswith(make_golden.SCRATCH):
+        if getattr(sys.modules[name], '__file__', '').startswith(reference_frontend.root()):
             del sys.modules[name]
 
 
-@pytest.mark.parametrize('module', MODULES)
-def test_reference_suite_on_our_runtime_objects(reference_with_our_runtime, module):
+@pytest.fixture
+def reference_with_our_runtime(reference_package):
+    """the reference front end over this package's wrappers + the reference-CPU shim (no GPU needed)"""
+    from oracle import ref_runtime
+    if not ref_runtime.available():
+        ref_runtime.build()
+    import qgate_b200.install
+    qgate_b200.install.install(reference_package, ref_runtime.module)
+    return reference_package
+
+
+@pytest.fixture
+def reference_on_cuda_library(reference_package, cuda_runtime):
+    """the reference front end over this package's wrappers + libqgate_b200.so (needs a B200)"""
+    import qgate_b200.install
+    qgate_b200.install.install(reference_package, cuda_runtime)
+    return reference_package
+
+
+def run_reference_module(module):
     mod = __import__('tests.' + module, fromlist=['*'])
     loader = unittest.TestLoader()
     suite = unittest.TestSuite()
@@ -68,6 +80,22 @@ def test_reference_suite_on_our_runtime_objects(reference_with_our_runtime, modu
     problems = ['{}: {}'.format(t.id(), tb.splitlines()[-1]) for t, tb in result.errors + result.failures]
     assert not problems, '\n'.join(problems)
     assert result.testsRun > 0
+    return result.testsRun
+
+
+@pytest.mark.parametrize('module', MODULES)
+def test_reference_suite_on_our_runtime_objects(reference_with_our_runtime, module):
+    run_reference_module(module)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('module', MODULES)
+def test_reference_suite_on_the_cuda_library(reference_on_cuda_library, module):
+    """The drop-in claim on the real thing: the reference's unmodified front end and its own
+    unittest classes, `qgate.simulator.cuda()` served by libqgate_b200.so on the B200."""
+    run_reference_module(module)
+    api = reference_on_cuda_library.simulator.cudaruntime.get_api()
+    assert api.backend_name == 'cuda-sm_100a'
 
 
 def test_simulator_sample_matches_reference_shot_for_shot(reference_with_our_runtime):
