@@ -63,8 +63,9 @@ def parse_args():
     ap.add_argument('--own-frontend', action='store_true',
                     help="e2e through this package's front end even when the reference's is installed")
     ap.add_argument('--option', action='append', default=[], help='engine option name=value')
-    ap.add_argument('--exchange', default='auto', choices=('auto', 'p2p', 'collective'),
-                    help='lane exchange engine of the sharded runs')
+    ap.add_argument('--exchange', default='auto', choices=('auto', 'p2p', 'p2p_inplace', 'collective'),
+                    help='lane exchange engine of the sharded runs (p2p pushes into spare buffers when '
+                         'memory allows; p2p_inplace forces the in-place swap kernel)')
     return ap.parse_args()
 
 
@@ -467,7 +468,8 @@ def main():
     # -- device-timed leg: native layer, gates queued first, events around the flush ------------
     if distributed:
         from qgate_b200 import dist as qdist
-        runtime = qdist.runtime(cudaruntime, exchange=args.exchange)
+        runtime = qdist.runtime(cudaruntime, exchange='p2p' if args.exchange == 'p2p_inplace' else args.exchange,
+                                push=args.exchange != 'p2p_inplace')
         runtime.ctx.bind_stream()              # NCCL work and the engine share this stream
         runtime.ctx.timing = True
         stream = runtime.ctx.stream
@@ -489,7 +491,9 @@ def main():
         if dstats['exchanges']:
             # bytes each GPU sends (= receives) per exchange over its NVLink ports
             gbs = dstats['exchange_bytes'] / (exch_ms * 1e-3) / 1e9
-            nvlink = {'exchange': runtime.ctx.exchange, 'exchanges_per_step': dstats['exchanges'] / args.steps,
+            nvlink = {'exchange': runtime.ctx.exchange + (' (push into spare buffers)' if dstats.get('push_exchanges') else
+                                                          ' (in place)' if runtime.ctx.exchange == 'p2p' else ''),
+                      'exchanges_per_step': dstats['exchanges'] / args.steps,
                       'lanes_per_exchange': dstats['exchange_lanes'] / dstats['exchanges'],
                       'local_swaps_per_step': dstats['local_swaps'] / args.steps,
                       'bytes_per_gpu_per_direction_per_step': dstats['exchange_bytes'] // args.steps,
@@ -535,7 +539,8 @@ def main():
             q, ops = circuits.random_u3_cx(S, n, args.depth, seed=args.seed)
 
             def make_sim():
-                prefs = {'sharding': {'exchange': args.exchange}} if distributed else {}
+                prefs = {'sharding': {'exchange': 'p2p' if args.exchange == 'p2p_inplace' else args.exchange,
+                                      'push': args.exchange != 'p2p_inplace'}} if distributed else {}
                 return qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static, **prefs)
             api_name = 'qgate_b200.simulator.cuda().run(circuit); qubits.calc_probability; qubits.states[:4096]'
         e2e_steps = max(1, min(args.steps, 3))

@@ -230,6 +230,14 @@ int qgb_ipc_close(uint64_t base_ptr);
  * (all ranks idle on this state before and after). */
 int qgb_qstates_exchange_p2p(qgb_handle qstates, const uint64_t *peer_ptrs, int k,
                              const int *victim_lanes, int my_sel);
+/* The push variant of the exchange: ranks write their outgoing amplitudes into each other's SPARE
+ * buffers (peer_alt_ptrs[j] = spare buffer of the rank whose selector bits equal j; the caller's
+ * own spare buffer at j == my_sel), then every rank makes its spare buffer the state vector.
+ * Write-only NVLink traffic; needs twice the shard in memory (qgb_qstates_exchange_p2p is the
+ * in-place fallback).  qgb_qstates_ipc_export_alt exports the spare buffer (allocating it). */
+int qgb_qstates_ipc_export_alt(qgb_handle qstates, void *handle64, int64_t *offset);
+int qgb_qstates_exchange_push(qgb_handle qstates, const uint64_t *peer_alt_ptrs, int k,
+                              const int *victim_lanes, int my_sel);
 
 /* ---- instrumentation (no reference counterpart) --------------------------- */
 

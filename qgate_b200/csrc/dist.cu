@@ -115,7 +115,60 @@ exchange_p2p_kernel(uint4 *__restrict__ local, const __grid_constant__ ExchangeP
     }
 }
 
+/* Push variant: every rank WRITES its outgoing amplitudes straight into the spare buffers of the
+ * ranks that will own them (and copies what it keeps into its own spare buffer); afterwards every
+ * rank flips to its spare buffer.  Write-only NVLink traffic (posted stores, no read round trips),
+ * one 16-byte local load and one store per unit, and almost no index arithmetic: the destination
+ * index is the source index with the victim bits replaced by this rank's selector bits — a
+ * constant — and the destination rank is the source index's victim bits.  Needs the spare buffer
+ * (twice the shard in memory); exchange_p2p_kernel above is the in-place fallback for shards that
+ * fill the GPU (QFT-35 on 4 GPUs: 128 GiB per shard). */
+__global__ void __launch_bounds__(256)
+exchange_push_kernel(const uint4 *__restrict__ local, const __grid_constant__ ExchangeParams ep) {
+    const int k = ep.k;
+    const uint64_t n_units = 1ull << ep.n_unit_bits;
+    uint64_t vmask = 0, sbits = 0;
+    for (int i = 0; i < k; ++i) {
+        vmask |= 1ull << ep.victim[i];
+        sbits |= (uint64_t)((ep.my_sel >> i) & 1) << ep.victim[i];
+    }
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    constexpr int UNROLL = 8;
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; t + (UNROLL - 1) * stride < n_units; t += UNROLL * stride) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = __ldcs(local + t + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint64_t i = t + u * stride;
+            int j = 0;
+#pragma unroll
+            for (int b = 0; b < QGB_MAX_EXCHANGE_LANES; ++b)
+                if (b < k) j |= (int)((i >> ep.victim[b]) & 1ull) << b;
+            uint4 *dst = reinterpret_cast<uint4 *>(ep.peer[j]);
+            __stcs(dst + ((i & ~vmask) | sbits), v[u]);
+        }
+    }
+    for (; t < n_units; t += stride) {
+        int j = 0;
+        for (int b = 0; b < k; ++b) j |= (int)((t >> ep.victim[b]) & 1ull) << b;
+        uint4 *dst = reinterpret_cast<uint4 *>(ep.peer[j]);
+        dst[(t & ~vmask) | sbits] = local[t];
+    }
+}
+
 } // namespace
+
+cudaError_t launch_exchange_push(const void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream) {
+    const uint64_t n_units = 1ull << ep.n_unit_bits;
+    uint64_t blocks = (n_units + 256 * 8 - 1) / (256 * 8);
+    const uint64_t cap = (uint64_t)(sm_count > 0 ? sm_count : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    exchange_push_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(local), ep);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_exchange_p2p(void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream) {
     const int rest_bits = ep.n_unit_bits - ep.k - 1;

@@ -915,6 +915,19 @@ int qgb_qstates_ipc_export(qgb_handle h, void *handle64, int64_t *offset) {
     QGB_CATCH
 }
 
+int qgb_qstates_ipc_export_alt(qgb_handle h, void *handle64, int64_t *offset) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (!qs->d_alt) qs->d_alt = g.pool.alloc(qs->bytes());
+    std::swap(qs->d_amp, qs->d_alt); /* export the spare buffer through the same code path */
+    const int rc = qgb_qstates_ipc_export(h, handle64, offset);
+    std::swap(qs->d_amp, qs->d_alt);
+    if (rc != QGB_OK) return rc;
+    QGB_CATCH
+}
+
 int qgb_ipc_open(const void *handle64, uint64_t *base_ptr) {
     QGB_TRY
     require_init();
@@ -982,6 +995,36 @@ int qgb_qstates_exchange_p2p(qgb_handle h, const uint64_t *peer_ptrs, int k, con
     flush(qs);
     CUDA_CHECK(launch_exchange_p2p(qs->d_amp, ep, g.sm_count, g.stream));
     g.stats.kernel_launches += 1;
+    QGB_CATCH
+}
+
+int qgb_qstates_exchange_push(qgb_handle h, const uint64_t *peer_alt_ptrs, int k, const int *victim_lanes,
+                              int my_sel) {
+    QGB_TRY
+    require_init();
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (!qs->d_alt) fail(QGB_ERR_RUNTIME, "qstates has no spare buffer.");
+    if (k < 1 || k > QGB_MAX_EXCHANGE_LANES) fail(QGB_ERR_INVALID, "exchange of %d lanes is not supported.", k);
+    if (my_sel < 0 || my_sel >= (1 << k)) fail(QGB_ERR_INVALID, "bad exchange selector.");
+    const int unit_shift = qs->prec == QGB_PREC_FP64 ? 0 : 1; /* 16-byte units */
+    ExchangeParams ep;
+    ep.k = k;
+    ep.my_sel = my_sel;
+    ep.n_unit_bits = qs->n_lanes - unit_shift;
+    ep.split = -1;
+    for (int i = 0; i < k; ++i) {
+        check_lane(qs, victim_lanes[i]);
+        if (victim_lanes[i] < unit_shift || (i > 0 && victim_lanes[i] <= victim_lanes[i - 1]))
+            fail(QGB_ERR_INVALID, "victim lanes must ascend and lie above the 16-byte unit.");
+        ep.victim[i] = victim_lanes[i] - unit_shift;
+    }
+    for (int j = 0; j < (1 << k); ++j) ep.peer[j] = reinterpret_cast<void *>(peer_alt_ptrs[j]);
+    if (ep.peer[my_sel] != qs->d_alt) fail(QGB_ERR_INVALID, "own spare buffer expected at the rank's selector.");
+    flush(qs);
+    CUDA_CHECK(launch_exchange_push(qs->d_amp, ep, g.sm_count, g.stream));
+    g.stats.kernel_launches += 1;
+    std::swap(qs->d_amp, qs->d_alt); /* every rank of the exchange does the same */
     QGB_CATCH
 }
 

@@ -131,5 +131,8 @@ struct ExchangeParams {
     void *peer[1 << QGB_MAX_EXCHANGE_LANES]; /* peer[j]: shard of the rank whose bits equal j   */
 };
 cudaError_t launch_exchange_p2p(void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream);
+/* push variant: ep.peer[j] = SPARE buffer of the rank whose selector bits equal j (this rank's own
+ * spare buffer for j == my_sel); `local` is only read */
+cudaError_t launch_exchange_push(const void *local, const ExchangeParams &ep, int sm_count, cudaStream_t stream);
 
 } // namespace qgb

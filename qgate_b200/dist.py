@@ -88,7 +88,7 @@ class Gate:
 
 
 class DistContext:
-    def __init__(self, local_module, group=None, exchange='auto', shard_min_lanes=None):
+    def __init__(self, local_module, group=None, exchange='auto', shard_min_lanes=None, push=True):
         if not dist.is_initialized():
             raise RuntimeError('torch.distributed is not initialized.')
         self.local = local_module
@@ -102,11 +102,23 @@ class DistContext:
         self.on_cuda = self.api.backend_name.startswith('cuda')
         self.device = torch.device('cuda', torch.cuda.current_device()) if self.on_cuda \
             else torch.device('cpu')
+        # The control plane (scalars, handles, barriers) follows the process group's backend: NCCL
+        # works on device tensors, in stream order; gloo on host tensors.  gloo + the CUDA engine is
+        # the "several ranks on ONE GPU" mode: NCCL refuses two ranks per device, CUDA IPC does not,
+        # so the p2p exchange kernel still moves the amplitudes (tests/test_dist_shared_gpu.py; the
+        # reference's logical devices on one GPU, tests/test_multidevice.py:13-21).
+        self.comm_cuda = self.on_cuda and dist.get_backend(group) == 'nccl'
+        self.comm_device = self.device if self.comm_cuda else torch.device('cpu')
         if exchange == 'auto':
             exchange = 'p2p' if self.on_cuda else 'collective'
         if exchange not in ('p2p', 'collective'):
             raise ValueError('exchange must be p2p or collective.')
+        if exchange == 'collective' and self.on_cuda and not self.comm_cuda:
+            raise ValueError('the collective exchange engine on GPUs needs the NCCL backend.')
         self.exchange = exchange
+        # p2p engine: ranks PUSH into each other's spare buffers (write-only NVLink traffic) when
+        # every rank can afford a spare buffer, else they swap in place (dist.cu)
+        self.push = bool(push)
         if shard_min_lanes is None:
             shard_min_lanes = 24 if self.on_cuda else 12
         self.shard_min_lanes = max(int(shard_min_lanes), 2 * self.g + 2)
@@ -133,21 +145,25 @@ class DistContext:
 
     def device_barrier(self):
         """Orders the ranks ON THE STREAM (no host sync on GPUs): a 1-element all_reduce."""
+        if self.on_cuda and not self.comm_cuda:
+            torch.cuda.synchronize()                   # host-side control plane: drain, then meet
+            dist.barrier(group=self.group)
+            return
         with self.stream_ctx():
             if self._barrier_buf is None:
-                self._barrier_buf = torch.zeros(1, dtype=torch.float32, device=self.device)
+                self._barrier_buf = torch.zeros(1, dtype=torch.float32, device=self.comm_device)
             dist.all_reduce(self._barrier_buf, group=self.group)
 
     def all_reduce_sum(self, value):
         with self.stream_ctx():
-            t = torch.tensor([value], dtype=torch.float64, device=self.device)
+            t = torch.tensor([value], dtype=torch.float64, device=self.comm_device)
             dist.all_reduce(t, group=self.group)
             return float(t.item())
 
     def all_gather_floats(self, value):
         with self.stream_ctx():
-            t = torch.tensor([value], dtype=torch.float64, device=self.device)
-            out = torch.empty(self.world, dtype=torch.float64, device=self.device)
+            t = torch.tensor([value], dtype=torch.float64, device=self.comm_device)
+            out = torch.empty(self.world, dtype=torch.float64, device=self.comm_device)
             dist.all_gather_into_tensor(out, t, group=self.group)
             return out.cpu().numpy()
 
@@ -156,21 +172,34 @@ class DistContext:
         flat = arr.view(np.float64) if arr.dtype == np.complex128 else \
             arr.view(np.float32) if arr.dtype == np.complex64 else arr
         with self.stream_ctx():
-            t = torch.from_numpy(flat).to(self.device)
+            t = torch.from_numpy(flat).to(self.comm_device)
             dist.all_reduce(t, group=self.group)
             flat[...] = t.cpu().numpy()
         return arr
 
+    def all_gather_shards(self, whole, part):
+        """whole = concatenation over the ranks of `part` (tensors over engine memory)."""
+        with self.stream_ctx():
+            if self.on_cuda and not self.comm_cuda:    # host-side control plane: stage through it
+                self.stream.synchronize()
+                gathered = torch.empty(whole.numel(), dtype=whole.dtype)
+                dist.all_gather_into_tensor(gathered, part.cpu(), group=self.group)
+                whole.copy_(gathered)
+            else:
+                dist.all_gather_into_tensor(whole, part, group=self.group)
+            if self.on_cuda:
+                self.stream.synchronize()
+
     def broadcast_float(self, value):
         with self.stream_ctx():
-            t = torch.tensor([value], dtype=torch.float64, device=self.device)
+            t = torch.tensor([value], dtype=torch.float64, device=self.comm_device)
             dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0,
                            group=self.group)
             return float(t.item())
 
     def broadcast_array(self, arr):
         with self.stream_ctx():
-            t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device)
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(self.comm_device)
             dist.broadcast(t, src=dist.get_global_rank(self.group, 0) if self.group else 0,
                            group=self.group)
             return t.cpu().numpy()
@@ -206,6 +235,7 @@ class DistQubitStates:
         self.perm = []                       # logical lane -> physical lane
         self.pending = []
         self.peers = None                    # p2p: mapped pointers of all ranks' shards
+        self.peers_alt = None                # ... and of their spare buffers (push exchange), or None
         self.peer_bases = []                 # the IPC mappings behind them (closed on delete)
         self.lane_states = []
 
@@ -240,6 +270,7 @@ class DistQubitStates:
                 except Exception:
                     pass
         self.peers = None
+        self.peers_alt = None
         self.peer_bases = []
 
     def get_n_lanes(self):
@@ -549,11 +580,18 @@ class DistQubitProcessor:
             ev0.record(ctx.stream)
         if ctx.exchange == 'p2p':
             self._ensure_peers(qs)
-            peer_ptrs = (C.c_uint64 * (1 << k))(*[qs.peers[rank_of(sel)] for sel in range(1 << k)])
+            table = qs.peers_alt if qs.peers_alt is not None else qs.peers
+            peer_ptrs = (C.c_uint64 * (1 << k))(*[table[rank_of(sel)] for sel in range(1 << k)])
             ctx.device_barrier()                 # all ranks' passes are ahead of the kernel
             with ctx.stream_ctx():
-                self.api.call('qgb_qstates_exchange_p2p', qs.local.ptr, peer_ptrs, k,
-                              (C.c_int * k)(*victims), my_sel)
+                if qs.peers_alt is not None:     # push into the spare buffers, then everybody flips
+                    self.api.call('qgb_qstates_exchange_push', qs.local.ptr, peer_ptrs, k,
+                                  (C.c_int * k)(*victims), my_sel)
+                    qs.peers, qs.peers_alt = qs.peers_alt, qs.peers
+                    ctx.stats['push_exchanges'] = ctx.stats.get('push_exchanges', 0) + 1
+                else:
+                    self.api.call('qgb_qstates_exchange_p2p', qs.local.ptr, peer_ptrs, k,
+                                  (C.c_int * k)(*victims), my_sel)
             ctx.device_barrier()                 # nobody touches its shard while a peer still does
         else:
             src = qs.tensor()
@@ -601,18 +639,44 @@ class DistQubitProcessor:
         if qs.peers is not None:
             return
         ctx = self.ctx
+        qs.peers, bases = self._map_peers(qs, 'qgb_qstates_ipc_export')
+        qs.peer_bases = bases
+        qs.peers_alt = None
+        if ctx.push:
+            # the push exchange needs a spare buffer on EVERY rank (twice the shard): ask, agree
+            handle = (C.c_ubyte * 64)()
+            offset = C.c_int64(0)
+            try:
+                self.api.call('qgb_qstates_ipc_export_alt', qs.local.ptr, handle, C.byref(offset))
+                mine = 1.
+            except RuntimeError:                 # out of device memory: swap in place instead
+                mine = 0.
+            everyone = ctx.all_gather_floats(mine)
+            if everyone.min() > 0.:
+                qs.peers_alt, alt_bases = self._map_peers(qs, 'qgb_qstates_ipc_export_alt')
+                qs.peer_bases = qs.peer_bases + alt_bases
+
+    def _map_peers(self, qs, export_fn):
+        """IPC-map one buffer (the shard or its spare) of every rank; returns ([pointer per rank],
+        [mappings to close])."""
+        ctx = self.ctx
         handle = (C.c_ubyte * 64)()
         offset = C.c_int64(0)
-        self.api.call('qgb_qstates_ipc_export', qs.local.ptr, handle, C.byref(offset))
+        self.api.call(export_fn, qs.local.ptr, handle, C.byref(offset))
         # everything on the engine's stream, the host read included: a read issued on another
         # stream would race with the all-gather and open a garbage handle
         with ctx.stream_ctx():
             mine = torch.tensor(list(bytes(handle)) + [offset.value], dtype=torch.int64,
-                                device=ctx.device)
-            everyone = torch.empty(ctx.world * 65, dtype=torch.int64, device=ctx.device)
+                                device=ctx.comm_device)
+            everyone = torch.empty(ctx.world * 65, dtype=torch.int64, device=ctx.comm_device)
             dist.all_gather_into_tensor(everyone, mine, group=ctx.group)
             table = everyone.cpu().numpy().reshape(ctx.world, 65)
-        own_ptr, _ = qs.data_ptr()
+        if export_fn.endswith('_alt'):
+            own = C.c_uint64(0)
+            self.api.call('qgb_qstates_alt_buffer', qs.local.ptr, C.byref(own))
+            own_ptr = own.value
+        else:
+            own_ptr, _ = qs.data_ptr()
         peers, bases = [], []
         for r in range(ctx.world):
             if r == ctx.rank:
@@ -623,8 +687,7 @@ class DistQubitProcessor:
             self.api.call('qgb_ipc_open', raw, C.byref(base))
             bases.append(base.value)
             peers.append(base.value + int(table[r, 64]))
-        qs.peers = peers
-        qs.peer_bases = bases
+        return peers, bases
 
     # -- observers ----------------------------------------------------------------------------
     def calc_probability(self, qs, lane):
@@ -681,10 +744,7 @@ class DistQubitProcessor:
             ptr, nbytes = C.c_uint64(0), C.c_int64(0)
             self.api.call('qgb_qstates_data_ptr', tmp.ptr, C.byref(ptr), C.byref(nbytes))
             part = _tensor_view(ptr.value, nbytes.value, self.ctx.on_cuda, self.ctx.device)
-            with self.ctx.stream_ctx():
-                dist.all_gather_into_tensor(qs0.tensor(), part, group=self.ctx.group)
-                if self.ctx.on_cuda:
-                    self.ctx.stream.synchronize()
+            self.ctx.all_gather_shards(qs0.tensor(), part)
             tmp.delete()
         qs0.perm = rest_perm
         qs0.pending = []
@@ -700,10 +760,7 @@ class DistQubitProcessor:
         ptr, nbytes = C.c_uint64(0), C.c_int64(0)
         self.api.call('qgb_qstates_data_ptr', tmp.ptr, C.byref(ptr), C.byref(nbytes))
         whole = _tensor_view(ptr.value, nbytes.value, ctx.on_cuda, ctx.device)
-        with ctx.stream_ctx():
-            dist.all_gather_into_tensor(whole, src.tensor(), group=ctx.group)
-            if ctx.on_cuda:
-                ctx.stream.synchronize()
+        ctx.all_gather_shards(whole, src.tensor())
         return tmp
 
     def join(self, qs, qs_list, n_new):
@@ -798,7 +855,7 @@ class DistSamplingPool:
             n_local_bits = self.n_pool_lanes - ctx.g
             obs[mine] = local | (np.int64(ctx.rank) << np.int64(n_local_bits))
         with ctx.stream_ctx():
-            t = torch.from_numpy(obs).to(ctx.device)
+            t = torch.from_numpy(obs).to(ctx.comm_device)
             dist.all_reduce(t, group=ctx.group)
             obs = t.cpu().numpy()
         for pos in self.empty_lanes:                    # deposit a 0 at every empty lane
