@@ -106,7 +106,10 @@ def test_sharded_cuda_matches_reference(case, exchange, ref_runtime):
             assert np.array_equal(got[key], want[key]), (rank, key)
         if 'bits' in want:
             assert np.array_equal(got['bits'], want['bits']), rank
-XX
+    if case in ('random', 'zoo', 'grover', 'mcz'):
+        assert results[0]['stats']['exchanges'] > 0, 'no lane exchange was exercised'
+        pushes = results[0]['stats'].get('push_exchanges', 0)
+        assert (pushes == results[0]['stats']['exchanges']) if exchange == 'p2p' else pushes == 0
 
 
 @pytest.mark.parametrize('exchange', ('p2p', 'collective'))

@@ -113,7 +113,9 @@ def test_ranks_sharing_one_gpu_match_reference(world, case, push, ref_runtime):
         if 'bits' in want:
             assert np.array_equal(got['bits'], want['bits']), rank
     if case in ('random', 'zoo', 'grover', 'mcz'):
-XX
+        st = results[0]['stats']
+        assert st['exchanges'] > 0, 'no lane exchange was exercised'
+        assert st.get('push_exchanges', 0) == (st['exchanges'] if push else 0)
         if world >= 4 and case == 'random':
             assert st['exchange_lanes'] > st['exchanges'], 'no multi-lane exchange was exercised'
 
