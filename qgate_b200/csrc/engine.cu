@@ -309,8 +309,11 @@ int min_tile_lanes(int prec) { return prec == QGB_PREC_FP64 ? 3 + 5 : 4 + 5; }
 
 /* cap on the summed op cost of a pass (sheared 2x2 = 3, direct 2x2 = 4, diagonal / exchange = 1) */
 int default_max_cost(bool fp32, bool shear) {
-    (void)fp32;
-    return shear ? 21 : 24;
+    /* measured on B200 at 30 qubits, sustained (power-capped) runs, profiles/r2c: complex128 8 sheared
+     * gates per pass = 2.74e12 updates/s at 0.78 of the HBM roofline (7 gates: 2.72e12 at 0.79, 9:
+     * 2.69e12 at 0.74); complex64 7 gates per pass = 4.9e12 at 0.71 (8: 5.05e12 at 0.69) */
+    if (!shear) return 24;
+    return fp32 ? 21 : 24;
 }
 
 template <typename real>
@@ -322,9 +325,11 @@ void flush_tiled(QStates *qs) {
     cfg.T = (int)(fp32 ? g.opt.tile_lanes_fp32 : g.opt.tile_lanes_fp64);
     cfg.T = std::max(cfg.K + 5, std::min(cfg.T, cfg.K + 10));
     const int low_opt = (int)(fp32 ? g.opt.low_lanes_fp32 : g.opt.low_lanes_fp64);
-    /* runs of 512 bytes: a pass with few ops is HBM-bound and 128-byte runs (the TMA minimum) cost
-     * 27% of the DRAM bandwidth (5.95 vs 7.83 ms per complex128 pass at 30 qubits, profiles/r1za) */
-    const int low_auto = fp32 ? 6 : 5;
+    /* runs of 256 bytes.  128-byte runs (the TMA minimum) cost 27% of the DRAM bandwidth (7.83 vs
+     * 5.95 ms per complex128 pass at 30 qubits, profiles/r1za); 256-byte runs cost 2.5% against
+     * 512-byte ones but leave one more tile lane free for gates: 116 instead of 131 passes on the
+     * bench circuit, 2.93e12 instead of 2.74e12 updates/s at 0.74 of the roofline (profiles/r2d) */
+    const int low_auto = fp32 ? 5 : 4;
     cfg.L = low_opt > 0 ? low_opt : low_auto;
     const int n_buf = g.opt.tma_buffers == 0 ? (fp32 ? 3 : 2) : (g.opt.tma_buffers >= 3 ? 3 : 2);
     /* ops per pass: their matrices are staged in shared memory, their predicates are one bit each */
