@@ -253,9 +253,40 @@ typedef struct qgb_stats {
     int64_t tma_passes;           /* tile passes staged by TMA tensor-map copies      */
     int64_t shear_ops;            /* dense 2x2 gates applied as three in-place shears  */
     int64_t direct_ops;           /* dense 2x2 gates applied as a direct 2x2 product   */
+    int64_t native_swaps;         /* qgb_qproc_apply_swap calls (lane relabellings)     */
+    int64_t native_pauli_exps;    /* qgb_qproc_apply_pauli_expi calls                  */
 } qgb_stats;
 int qgb_stats_get(qgb_stats *out);
 int qgb_stats_reset(void);
+/* ---- "next" rows of the hot path ---------------------------------------
+ * What the reference's front end does in Python around the native calls above, as native calls.
+ *
+ * f-3  multi-qubit ops without their expansion into CX chains (qgate/model/expand.py:14-90):
+ *   qgb_qproc_apply_swap        Swap(a, b).  The reference applies three CX gates (three sweeps of
+ *                               the state); here the two lanes exchange their index bits in the
+ *                               qstates' lane map — no amplitude moves.
+ *   qgb_qproc_apply_pauli_expi  exp(i theta P), P a Pauli string (paulis[i] in {0: I, 1: X, 2: Y,
+ *                               3: Z} on lanes[i]), optionally controlled.  The reference applies
+ *                               basis changes + 2(k-1) CX gates + ExpiZ/ExpiI; here: the basis
+ *                               changes (1-qubit gates, merged into their neighbours) around ONE
+ *                               parity-phase diagonal op of the fused pass.
+ * f-1  batch submit (model_executor.py:80-175 + rop_executor.py:28-53 make one native call per
+ *      gate): qgb_qproc_apply_gates_batch queues n_ops gates in one call. */
+int qgb_qproc_apply_swap(qgb_handle qproc, qgb_handle qstates, int lane_a, int lane_b);
+int qgb_qproc_apply_pauli_expi(qgb_handle qproc, qgb_handle qstates, double theta, const int *lanes,
+                               const int *paulis, int n, const int *ctrl_lanes, int n_ctrl);
+#define QGB_GATE_MATRIX (-1)
+typedef struct qgb_gate_op {
+    int32_t gate_id;      /* index of the gate-matrix factory (qgb_gate_matrix), or QGB_GATE_MATRIX */
+    int32_t adjoint;
+    int32_t target;       /* local lane */
+    int32_t reserved;
+    uint64_t ctrl_mask;   /* bit l set: local lane l is a control */
+    double args[3];       /* factory arguments (gate_id >= 0) */
+    double mat8[8];       /* (re, im) of m00, m01, m10, m11 (gate_id == QGB_GATE_MATRIX) */
+} qgb_gate_op;
+int qgb_qproc_apply_gates_batch(qgb_handle qproc, qgb_handle qstates, const qgb_gate_op *ops, int64_t n_ops);
+
 /* force the deferred gate queue of one qstates onto the device (no host sync). */
 int qgb_qproc_flush(qgb_handle qproc, qgb_handle qstates);
 /* tuning knobs: "max_gates_per_pass", "tile_lanes_fp32", "tile_lanes_fp64",

@@ -361,6 +361,76 @@ int qgb_qproc_apply_gate_typed(qgb_handle qp, int gate_id, const double *args, i
     QGB_CATCH
 }
 
+/* The "next" rows on the reference runtime = what the reference's front end
+ * expands them into (qgate/model/expand.py:14-90), applied gate by gate. */
+int qgb_qproc_apply_swap(qgb_handle qp, qgb_handle qs, int lane_a, int lane_b) {
+    const int a[1] = {lane_a}, b[1] = {lane_b};
+    int rc = qgb_qproc_apply_gate_typed(qp, 4 /* X */, NULL, 0, 0, qs, b, 1, lane_a);
+    if (rc == QGB_OK) rc = qgb_qproc_apply_gate_typed(qp, 4, NULL, 0, 0, qs, a, 1, lane_b);
+    if (rc == QGB_OK) rc = qgb_qproc_apply_gate_typed(qp, 4, NULL, 0, 0, qs, b, 1, lane_a);
+    return rc;
+}
+
+int qgb_qproc_apply_pauli_expi(qgb_handle qp, qgb_handle qs, double theta, const int *lanes, const int *paulis,
+                               int n, const int *ctrl, int n_ctrl) {
+    /* basis changes, a CX chain onto the last non-identity factor, ExpiZ there, everything undone */
+    std::vector<int> active;
+    for (int i = 0; i < n; ++i)
+        if (paulis[i] != 0) active.push_back(i);
+    int rc = QGB_OK;
+    for (size_t k = 0; k < active.size() && rc == QGB_OK; ++k) {
+        const int i = active[k];
+        if (paulis[i] == 2) rc = qgb_qproc_apply_gate_typed(qp, 8 /* S */, NULL, 0, 1, qs, NULL, 0, lanes[i]);
+        if (rc == QGB_OK && paulis[i] != 3) rc = qgb_qproc_apply_gate_typed(qp, 7 /* H */, NULL, 0, 0, qs, NULL, 0, lanes[i]);
+    }
+    if (active.empty()) {
+        int free_lane = 0;
+        for (;; ++free_lane) {
+            bool used = false;
+            for (int c = 0; c < n_ctrl; ++c) used = used || ctrl[c] == free_lane;
+            if (!used) break;
+        }
+        return qgb_qproc_apply_gate_typed(qp, 13 /* ExpiI */, &theta, 1, 0, qs, ctrl, n_ctrl, free_lane);
+    }
+    const int last = lanes[active.back()];
+    for (size_t k = 0; k + 1 < active.size() && rc == QGB_OK; ++k) {
+        const int c[1] = {lanes[active[k]]};
+        rc = qgb_qproc_apply_gate_typed(qp, 4 /* X */, NULL, 0, 0, qs, c, 1, last);
+    }
+    if (rc == QGB_OK) rc = qgb_qproc_apply_gate_typed(qp, 14 /* ExpiZ */, &theta, 1, 0, qs, ctrl, n_ctrl, last);
+    for (size_t k = active.size() - 1; k-- > 0 && rc == QGB_OK;) {
+        const int c[1] = {lanes[active[k]]};
+        rc = qgb_qproc_apply_gate_typed(qp, 4, NULL, 0, 0, qs, c, 1, last);
+    }
+    for (size_t k = active.size(); k-- > 0 && rc == QGB_OK;) {
+        const int i = active[k];
+        if (paulis[i] != 3) rc = qgb_qproc_apply_gate_typed(qp, 7, NULL, 0, 0, qs, NULL, 0, lanes[i]);
+        if (rc == QGB_OK && paulis[i] == 2) rc = qgb_qproc_apply_gate_typed(qp, 8, NULL, 0, 0, qs, NULL, 0, lanes[i]);
+    }
+    return rc;
+}
+
+int qgb_qproc_apply_gates_batch(qgb_handle qp, qgb_handle qs, const qgb_gate_op *ops, int64_t n_ops) {
+    for (int64_t i = 0; i < n_ops; ++i) {
+        const qgb_gate_op &op = ops[i];
+        int ctrl[64], n_ctrl = 0;
+        for (int lane = 0; lane < 64; ++lane)
+            if ((op.ctrl_mask >> lane) & 1ull) ctrl[n_ctrl++] = lane;
+        int rc;
+        if (op.gate_id == QGB_GATE_MATRIX)
+            rc = n_ctrl ? qgb_qproc_apply_controlled_gate(qp, op.mat8, qs, ctrl, n_ctrl, op.target)
+                        : qgb_qproc_apply_gate(qp, op.mat8, qs, op.target);
+        else {
+            static const int n_args[16] = {3, 2, 1, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0};
+            if (op.gate_id < 0 || op.gate_id > 15) return fail(QGB_ERR_RUNTIME, "Unknown gate type.");
+            rc = qgb_qproc_apply_gate_typed(qp, op.gate_id, op.args, n_args[op.gate_id], op.adjoint, qs, ctrl, n_ctrl,
+                                            op.target);
+        }
+        if (rc != QGB_OK) return rc;
+    }
+    return QGB_OK;
+}
+
 int qgb_getter_new(int prec, qgb_handle *out) {
     QGB_TRY
     qgate::QubitsStatesGetter *g = NULL;

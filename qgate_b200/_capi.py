@@ -38,7 +38,7 @@ class Stats(C.Structure):
     _fields_ = [(name, C.c_int64) for name in (
         'kernel_launches', 'gates_submitted', 'gates_executed', 'tile_passes',
         'gate_amp_updates', 'pass_bytes', 'h2d_bytes', 'd2h_bytes', 'tma_passes', 'shear_ops',
-        'direct_ops')]
+        'direct_ops', 'native_swaps', 'native_pauli_exps')]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}
@@ -79,6 +79,9 @@ SIGNATURES = {
     'qgb_stats_get': [C.POINTER(Stats)],
     'qgb_stats_reset': [],
     'qgb_qproc_flush': [_h, _h],
+    'qgb_qproc_apply_swap': [_h, _h, _i, _i],
+    'qgb_qproc_apply_pauli_expi': [_h, _h, _d, _ip, _ip, _i, _ip, _i],
+    'qgb_qproc_apply_gates_batch': [_h, _h, _p, _i64],
     'qgb_set_option': [C.c_char_p, _i64],
     # sharding support
     'qgb_qstates_data_ptr': [_h, _hp, _i64p],
@@ -101,6 +104,19 @@ _NON_STATUS = {
     'qgb_backend_name': ([], C.c_char_p),
     'qgb_abi_version': ([], C.c_int),
 }
+
+
+class GateOp(C.Structure):
+    """qgb_gate_op of include/qgate_b200.h (one record of qgb_qproc_apply_gates_batch)."""
+    _fields_ = [('gate_id', C.c_int32), ('adjoint', C.c_int32), ('target', C.c_int32), ('reserved', C.c_int32),
+                ('ctrl_mask', C.c_uint64), ('args', C.c_double * 3), ('mat8', C.c_double * 8)]
+
+
+GATE_OP_DTYPE = np.dtype([('gate_id', np.int32), ('adjoint', np.int32), ('target', np.int32), ('reserved', np.int32),
+                          ('ctrl_mask', np.uint64), ('args', np.float64, (3,)), ('mat8', np.float64, (8,))])
+assert GATE_OP_DTYPE.itemsize == C.sizeof(GateOp)
+GATE_MATRIX = -1
+PAULI_CODES = {'ID': 0, 'X': 1, 'Y': 2, 'Z': 3}
 
 
 def exported_symbols():

@@ -174,6 +174,17 @@ struct QStates {
     int n_lanes = -1;
     void *d_amp = nullptr;
     void *d_alt = nullptr; /* spare array for out-of-place exchanges (sharded states only) */
+    /* lane map: lane l of the caller (the "local lane" of the reference's protocol) is bit perm[l]
+     * of the array index.  Identity until a native Swap: exchanging two lanes is exchanging two
+     * entries here, no amplitude moves (the reference expands a Swap into three
+     * CX gates = three state sweeps, model/expand.py:14-20).  Queued gates, kernels and the tables of
+     * a readout are in index-bit coordinates. */
+    std::vector<int> perm;
+    int phys(int lane) const { return perm[(size_t)lane]; }
+    void reset_perm() {
+        perm.resize((size_t)std::max(n_lanes, 0));
+        for (int l = 0; l < n_lanes; ++l) perm[(size_t)l] = l;
+    }
     std::vector<Gate> queue;
     size_t elem() const { return prec == QGB_PREC_FP64 ? 16 : 8; }
     size_t bytes() const { return elem() << n_lanes; }
@@ -389,7 +400,10 @@ void flush(QStates *qs) {
             flush_tiled<float>(qs);
     } else {
         for (const Gate &gt : qs->queue) {
-            if (gt.mux >= 0) {
+            if (gt.parity) {
+                CUDA_CHECK(launch_simple_parity(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.m + 6, gt.parity,
+                                                gt.ctrl_mask, g.stream));
+            } else if (gt.mux >= 0) {
                 /* multiplexed gate (host-side merging): m where lane mux is 0, m1 where it is 1 */
                 CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.target, 0,
                                               1ull << gt.mux, false, g.stream));
@@ -407,18 +421,30 @@ void flush(QStates *qs) {
     }
 }
 
+uint64_t control_mask(const QStates *qs, const int *ctrl, int n_ctrl, uint64_t forbidden) {
+    uint64_t mask = 0;
+    for (int i = 0; i < n_ctrl; ++i) {
+        check_lane(qs, ctrl[i]);
+        const uint64_t bit = 1ull << qs->phys(ctrl[i]);
+        if (bit & forbidden) fail(QGB_ERR_INVALID, "control lane equals target lane.");
+        mask |= bit;
+    }
+    return mask;
+}
+
+void submit_queued(QStates *qs, const Gate &gt, int n_ctrl);
+
 void submit_gate(QStates *qs, const double *mat8, const int *ctrl, int n_ctrl, int target) {
     check_allocated(qs);
     check_lane(qs, target);
     Gate gt;
     std::memcpy(gt.m, mat8, sizeof(gt.m));
-    gt.target = target;
-    gt.ctrl_mask = 0;
-    for (int i = 0; i < n_ctrl; ++i) {
-        check_lane(qs, ctrl[i]);
-        if (ctrl[i] == target) fail(QGB_ERR_INVALID, "control lane equals target lane.");
-        gt.ctrl_mask |= 1ull << ctrl[i];
-    }
+    gt.target = qs->phys(target);
+    gt.ctrl_mask = control_mask(qs, ctrl, n_ctrl, 1ull << gt.target);
+    submit_queued(qs, gt, n_ctrl);
+}
+
+void submit_queued(QStates *qs, const Gate &gt, int n_ctrl) {
     /* merging pays on the tiled path only; the one-kernel-per-gate path keeps the submitted gates */
     const bool tiled = !g.opt.exact && g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec);
     enqueue_gate(qs->queue, gt, g.opt.merge != 0 && tiled);
@@ -474,7 +500,7 @@ void build_gather(GatherParams &gp, int prec, const int *lane_tables, const int 
         for (int l = 0; l < qs->n_lanes; ++l) {
             if (p[l] < 0 || p[l] >= n_ext_lanes)
                 fail(QGB_ERR_INVALID, "external lane %d out of range [0, %d).", p[l], n_ext_lanes);
-            host[q].ext[l] = (int8_t)p[l];
+            host[q].ext[qs->phys(l)] = (int8_t)p[l]; /* the table is indexed by index bit */
         }
         p += n_per[q];
     }
@@ -740,6 +766,7 @@ int qgb_qproc_initialize_qstates(qgb_handle qp, qgb_handle h, int n_lanes) {
     if (n_lanes < 0 || n_lanes > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "n_lanes %d out of range.", n_lanes);
     free_qstates_buffer(qs);
     qs->n_lanes = n_lanes;
+    qs->reset_perm();
     qs->d_amp = g.pool.alloc(qs->bytes());
     QGB_CATCH
 }
@@ -751,6 +778,7 @@ int qgb_qproc_reset_qstates(qgb_handle qp, qgb_handle h) {
     QStates *qs = QS(h);
     check_allocated(qs);
     qs->queue.clear();
+    qs->reset_perm();
     CUDA_CHECK(launch_set_basis_state(qs->prec, qs->d_amp, 1ull << qs->n_lanes, 0, g.stream));
     g.stats.kernel_launches += 1;
     QGB_CATCH
@@ -764,7 +792,7 @@ int qgb_qproc_calc_probability(qgb_handle qp, qgb_handle h, int lane, double *pr
     check_allocated(qs);
     check_lane(qs, lane);
     flush(qs);
-    CUDA_CHECK(launch_prob0(qs->prec, qs->d_amp, qs->n_lanes, lane, g.d_partials, g.d_partials + 2048,
+    CUDA_CHECK(launch_prob0(qs->prec, qs->d_amp, qs->n_lanes, qs->phys(lane), g.d_partials, g.d_partials + 2048,
                             g.stream));
     g.stats.kernel_launches += 2;
     CUDA_CHECK(cudaMemcpyAsync(g.h_scalar, g.d_partials + 2048, sizeof(double), cudaMemcpyDeviceToHost,
@@ -806,6 +834,14 @@ static void join_impl(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list
     dst->queue.clear();
     CUDA_CHECK(launch_join(dst->prec, dst->d_amp, dst->n_lanes, shift, (uint64_t)index_offset, jp, g.stream));
     g.stats.kernel_launches += 1;
+    /* the product keeps every source's array as it is: source k's lane l (its index bit perm[l])
+     * becomes the product's lane and index bit shift_k + ...; new lanes follow in order */
+    dst->reset_perm();
+    if (dst->n_lanes == n_total_lanes)
+        for (int k = 0; k < n_src; ++k) {
+            const QStates *src = QS(src_list[k]);
+            for (int l = 0; l < src->n_lanes; ++l) dst->perm[(size_t)(jp.shift[k] + l)] = jp.shift[k] + src->phys(l);
+        }
 }
 
 int qgb_qproc_join(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list, int n_src, int n_new_lanes) {
@@ -1043,7 +1079,7 @@ int qgb_qproc_decohere(qgb_handle qp, int value, double prob, qgb_handle h, int 
     flush(qs);
     /* CPUQubitProcessor.cpp:227,235: the factor is computed in double, then cast */
     const double norm = (value == 0) ? 1. / std::sqrt(prob) : 1. / std::sqrt(1. - prob);
-    CUDA_CHECK(launch_decohere(qs->prec, qs->d_amp, qs->n_lanes, lane, value ? 1 : 0, norm, g.stream));
+    CUDA_CHECK(launch_decohere(qs->prec, qs->d_amp, qs->n_lanes, qs->phys(lane), value ? 1 : 0, norm, g.stream));
     g.stats.kernel_launches += 1;
     QGB_CATCH
 }
@@ -1066,10 +1102,20 @@ int qgb_qproc_decohere_and_separate(qgb_handle qp, int value, double prob, qgb_h
     qs0->queue.clear();
     qs1->queue.clear();
     const double norm = (value == 0) ? 1. / std::sqrt(prob) : 1. / std::sqrt(1. - prob);
-    CUDA_CHECK(launch_decohere_separate(qs->prec, qs0->d_amp, qs->d_amp, qs->n_lanes, lane, value ? 1 : 0,
+    const int p = qs->phys(lane);
+    CUDA_CHECK(launch_decohere_separate(qs->prec, qs0->d_amp, qs->d_amp, qs->n_lanes, p, value ? 1 : 0,
                                         norm, g.stream));
     CUDA_CHECK(launch_set_basis_state(qs1->prec, qs1->d_amp, 2, value ? 1 : 0, g.stream));
     g.stats.kernel_launches += 2;
+    /* the remainder: `lane` leaves, the caller's lanes above it move down by one; index bit p
+     * leaves, the index bits above it move down by one */
+    qs0->perm.clear();
+    for (int l = 0; l < qs->n_lanes; ++l) {
+        if (l == lane) continue;
+        const int q = qs->phys(l);
+        qs0->perm.push_back(q > p ? q - 1 : q);
+    }
+    qs1->reset_perm();
     QGB_CATCH
 }
 
@@ -1081,7 +1127,7 @@ int qgb_qproc_apply_reset(qgb_handle qp, qgb_handle h, int lane) {
     check_allocated(qs);
     check_lane(qs, lane);
     flush(qs);
-    CUDA_CHECK(launch_apply_reset(qs->prec, qs->d_amp, qs->n_lanes, lane, g.stream));
+    CUDA_CHECK(launch_apply_reset(qs->prec, qs->d_amp, qs->n_lanes, qs->phys(lane), g.stream));
     g.stats.kernel_launches += 1;
     QGB_CATCH
 }
@@ -1111,6 +1157,106 @@ int qgb_qproc_apply_gate_typed(qgb_handle qp, int gate_id, const double *args, i
     double m[8];
     gate_matrix(gate_id, args, adjoint, m);
     submit_gate(QS(h), m, ctrl, n_ctrl, target);
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_swap(qgb_handle qp, qgb_handle h, int lane_a, int lane_b) {
+    QGB_TRY
+    QP(qp);
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    check_lane(qs, lane_a);
+    check_lane(qs, lane_b);
+    std::swap(qs->perm[(size_t)lane_a], qs->perm[(size_t)lane_b]); /* gates queued so far keep their index bits */
+    g.stats.gates_submitted += 1;
+    g.stats.native_swaps += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_pauli_expi(qgb_handle qp, qgb_handle h, double theta, const int *lanes, const int *paulis,
+                               int n, const int *ctrl, int n_ctrl) {
+    QGB_TRY
+    QP(qp);
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (n < 0 || n > QGB_MAX_LANES) fail(QGB_ERR_INVALID, "bad number of Pauli factors.");
+    uint64_t zmask = 0;
+    for (int i = 0; i < n; ++i) {
+        check_lane(qs, lanes[i]);
+        if (paulis[i] < 0 || paulis[i] > 3) fail(QGB_ERR_INVALID, "Pauli code %d (0 = I, 1 = X, 2 = Y, 3 = Z).", paulis[i]);
+        const uint64_t bit = 1ull << qs->phys(lanes[i]);
+        if (zmask & bit) fail(QGB_ERR_INVALID, "lane %d appears twice in the Pauli string.", lanes[i]);
+        if (paulis[i] != 0) zmask |= bit;
+    }
+    const uint64_t cmask = control_mask(qs, ctrl, n_ctrl, zmask);
+    /* exp(i theta P) = V exp(i theta Z..Z) V^+, V = product over the X factors of H and over the Y
+     * factors of S H (H Z H = X, S X S^+ = Y); the basis changes need no controls (they cancel
+     * where the middle does not act) and merge into the neighbouring gates of their lanes */
+    double mh[8], ms[8], msd[8];
+    gate_matrix(7 /* H */, nullptr, 0, mh);
+    gate_matrix(8 /* S */, nullptr, 0, ms);
+    gate_matrix(8 /* S */, nullptr, 1, msd);
+    for (int i = 0; i < n; ++i) {
+        if (paulis[i] == 2) submit_gate(qs, msd, nullptr, 0, lanes[i]);
+        if (paulis[i] == 1 || paulis[i] == 2) submit_gate(qs, mh, nullptr, 0, lanes[i]);
+    }
+    Gate gt;
+    for (int e = 0; e < 8; ++e) gt.m[e] = 0.;
+    gt.m[0] = std::cos(theta), gt.m[1] = std::sin(theta);
+    if (zmask) {
+        gt.m[6] = std::cos(theta), gt.m[7] = -std::sin(theta);
+        gt.target = __builtin_ctzll(zmask);
+        gt.parity = zmask;
+        gt.ctrl_mask = cmask;
+    } else {
+        /* the identity string: exp(i theta) on every amplitude the controls select */
+        gt.m[6] = gt.m[0], gt.m[7] = gt.m[1];
+        int free_lane = 0;
+        while (free_lane < qs->n_lanes && ((cmask >> free_lane) & 1ull)) ++free_lane;
+        if (free_lane < qs->n_lanes) {
+            gt.target = free_lane;
+            gt.ctrl_mask = cmask;
+        } else { /* every lane is a control: one of them becomes the target of diag(1, e^{i theta}) */
+            gt.target = 0;
+            gt.ctrl_mask = cmask & ~1ull;
+            gt.m[0] = 1., gt.m[1] = 0.;
+        }
+    }
+    submit_queued(qs, gt, n_ctrl);
+    for (int i = n - 1; i >= 0; --i) {
+        if (paulis[i] == 1 || paulis[i] == 2) submit_gate(qs, mh, nullptr, 0, lanes[i]);
+        if (paulis[i] == 2) submit_gate(qs, ms, nullptr, 0, lanes[i]);
+    }
+    g.stats.native_pauli_exps += 1;
+    QGB_CATCH
+}
+
+int qgb_qproc_apply_gates_batch(qgb_handle qp, qgb_handle h, const qgb_gate_op *ops, int64_t n_ops) {
+    QGB_TRY
+    QP(qp);
+    QStates *qs = QS(h);
+    check_allocated(qs);
+    if (n_ops < 0) fail(QGB_ERR_INVALID, "negative number of gates.");
+    for (int64_t i = 0; i < n_ops; ++i) {
+        const qgb_gate_op &op = ops[i];
+        double m[8];
+        if (op.gate_id == QGB_GATE_MATRIX) {
+            std::memcpy(m, op.mat8, sizeof(m));
+        } else {
+            const int want = gate_matrix_n_args(op.gate_id);
+            if (want < 0) fail(QGB_ERR_RUNTIME, "Unknown gate type.");
+            gate_matrix(op.gate_id, op.args, op.adjoint, m);
+        }
+        check_lane(qs, op.target);
+        int ctrl[64];
+        int n_ctrl = 0;
+        for (int lane = 0; lane < 64; ++lane)
+            if ((op.ctrl_mask >> lane) & 1ull) {
+                if (lane >= qs->n_lanes) fail(QGB_ERR_INVALID, "control lane %d out of range [0, %d).", lane, qs->n_lanes);
+                ctrl[n_ctrl++] = lane;
+            }
+        submit_gate(qs, m, ctrl, n_ctrl, op.target);
+    }
     QGB_CATCH
 }
 
@@ -1242,7 +1388,7 @@ static void pool_set_source(Pool *p, int prec, const int *lane_tables, const int
         QStates *qs = QS(list[0]);
         check_allocated(qs);
         bool identity = qs->prec == prec && qs->n_lanes == n_lanes && n_per[0] == n_lanes;
-        for (int l = 0; identity && l < n_lanes; ++l) identity = lane_tables[l] == l;
+        for (int l = 0; identity && l < n_lanes; ++l) identity = lane_tables[l] == qs->phys(l);
         if (identity) {
             flush(qs);
             p->d_cum = static_cast<double *>(g.pool.alloc(sizeof(double) << n_lanes));

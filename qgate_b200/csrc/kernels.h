@@ -53,6 +53,11 @@ void tma_pass_phase_report(); /* no-op unless built with -DQGB_PHASE_TIMING */
 cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *mat8, int target,
                                uint64_t ctrl_mask, uint64_t zero_mask, bool exact, cudaStream_t stream);
 
+/* parity diagonal, one launch: a *= d0 / d1 by the parity of the index bits in `parity` (where the
+ * ctrl_mask bits are set) */
+cudaError_t launch_simple_parity(int prec, void *amp, int n_lanes, const double *d0, const double *d1, uint64_t parity,
+                                 uint64_t ctrl_mask, cudaStream_t stream);
+
 /* ---- state-vector maintenance ------------------------------------------------------ */
 cudaError_t launch_set_basis_state(int prec, void *amp, uint64_t n_amps, uint64_t one_at,
                                    cudaStream_t stream);

@@ -104,6 +104,22 @@ simple_gate_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_pairs
     amp[i1] = o1;
 }
 
+/* parity diagonal on a state too small for the fused pass: a *= d0 (even number of `parity` lanes set)
+ * or d1 (odd), where the control bits are set */
+template <typename real>
+__global__ void __launch_bounds__(256)
+simple_parity_kernel(typename Cplx<real>::type *__restrict__ amp, uint64_t n_amps, uint64_t parity, uint64_t ctrl_mask,
+                     real d0r, real d0i, real d1r, real d1i) {
+    typedef typename Cplx<real>::type cplx;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_amps || (i & ctrl_mask) != ctrl_mask) return;
+    cplx d;
+    const bool odd = __popcll(i & parity) & 1;
+    d.x = odd ? d1r : d0r;
+    d.y = odd ? d1i : d0i;
+    amp[i] = cmul_exact(d, amp[i]);
+}
+
 /* ---- reset to a basis state (CPUQubitProcessor.cpp:61-73) ----------------------------- */
 template <typename real>
 __global__ void set_one_kernel(typename Cplx<real>::type *amp, uint64_t one_at) {
@@ -562,6 +578,19 @@ cudaError_t launch_simple_gate(int prec, void *amp, int n_lanes, const double *m
             simple_gate_kernel<float, false><<<nblocks, nthr, 0, stream>>>(reinterpret_cast<float2 *>(amp), n_pairs, skip,
                                                                           1ull << target, ctrl_mask, m);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_simple_parity(int prec, void *amp, int n_lanes, const double *d0, const double *d1, uint64_t parity,
+                                 uint64_t ctrl_mask, cudaStream_t stream) {
+    const uint64_t n = 1ull << n_lanes;
+    const unsigned nblocks = (unsigned)((n + 255) / 256);
+    if (prec == 1)
+        simple_parity_kernel<double><<<nblocks, 256, 0, stream>>>(reinterpret_cast<double2 *>(amp), n, parity, ctrl_mask,
+                                                                 d0[0], d0[1], d1[0], d1[1]);
+    else
+        simple_parity_kernel<float><<<nblocks, 256, 0, stream>>>(reinterpret_cast<float2 *>(amp), n, parity, ctrl_mask,
+                                                                (float)d0[0], (float)d0[1], (float)d1[0], (float)d1[1]);
     return cudaGetLastError();
 }
 

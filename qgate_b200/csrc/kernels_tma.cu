@@ -436,7 +436,7 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
     case OPC_DIAG_REG: {
         const uint32_t regmask = op.regmask, regsel = op.regsel;
         real d0r, d0i, d1r, d1i;
-        m.factor(0, d0r, d0i); /* register-bit diagonals have no thread / tile selector: mm == mo */
+        m.factor(0, d0r, d0i); /* (of the block the thread / tile parity selected: parity diagonals) */
         m.factor(1, d1r, d1i);
         lean_phase<K>(a, d0r, d0i, regmask & ~regsel);
         lean_phase<K>(a, d1r, d1i, regmask & regsel);
@@ -507,7 +507,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         for (int o = st.op_begin; o < st.op_end; ++o) {
             const Op<real> &op = prog.op[o];
             if ((ebase & op.cmt) == op.cmt) act |= 1u << o;
-            if (ebase & op.tsel) sel_thr |= 1u << o;
+            if (__popc(ebase & op.tsel) & 1) sel_thr |= 1u << o; /* one bit, or the parity of several */
         }
     }
     if (tid == 0) {
@@ -607,9 +607,9 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         uint32_t eff = act, sel = sel_thr;
         for (int i = 0; i < prog.n_out; ++i) {
             const uint64_t cm = prog.out[i].ctrl_mask;
-            const int o = prog.out[i].op, lane = prog.out[i].sel_lane;
+            const int o = prog.out[i].op;
             if ((base & cm) != cm) eff &= ~(1u << o);
-            if (lane >= 0 && ((base >> lane) & 1ull)) sel |= 1u << o;
+            if (__popcll(base & prog.out[i].sel_mask) & 1) sel ^= 1u << o;
         }
 
         PH_MARK(ph_tail);

@@ -91,7 +91,7 @@ namespace {
 inline bool mat_is_diag(const double *m) { return m[2] == 0. && m[3] == 0. && m[4] == 0. && m[5] == 0.; }
 
 inline uint64_t touched_lanes(const Gate &p) {
-    return p.ctrl_mask | (1ull << p.target) | (p.mux >= 0 ? (1ull << p.mux) : 0ull);
+    return p.ctrl_mask | (1ull << p.target) | (p.mux >= 0 ? (1ull << p.mux) : 0ull) | p.parity;
 }
 
 /* does p act non-diagonally on `lane`?  (a control / multiplexer lane is acted on diagonally) */
@@ -143,7 +143,7 @@ bool shear_factor(const double *m, int s, ShearCoef &out) {
  *                              the result is dense (diagonal controlled gates stay cheap phases);
  *   anything else:             folds only into an identical-signature gate directly before it. */
 bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
-    if (merge && !queue.empty() && g.mux < 0) {
+    if (merge && !queue.empty() && g.mux < 0 && g.parity == 0) {
         const int n_ctrl = popcount64(g.ctrl_mask);
         if (n_ctrl <= 1) {
             const uint64_t tm = 1ull << g.target;
@@ -155,7 +155,7 @@ bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
                     if (c >= 0 && acts_nondiag_on(p, c)) break; /* g does not commute with p */
                     continue;
                 }
-                if (p.target != g.target) break;
+                if (p.target != g.target || p.parity) break;
                 if (c < 0) {
                     if (p.ctrl_mask == 0) { /* plain or multiplexed p */
                         matmul2(g.m, p.m, p.m);
@@ -179,7 +179,7 @@ bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
             }
         } else {
             Gate &p = queue.back();
-            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask && p.mux < 0) {
+            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask && p.mux < 0 && p.parity == 0) {
                 matmul2(g.m, p.m, p.m);
                 return true;
             }
@@ -222,7 +222,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         const bool diag = gate_is_diag(g);
         const uint64_t tm = 1ull << g.target;
         const uint64_t xq = diag ? 0 : tm;
-        const uint64_t zq = g.ctrl_mask | (diag ? tm : 0) | (g.mux >= 0 ? (1ull << g.mux) : 0ull);
+        const uint64_t zq = g.ctrl_mask | (diag ? gate_diag_lanes(g) : 0) | (g.mux >= 0 ? (1ull << g.mux) : 0ull);
         bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
         const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4));
         /* op slots: a sheared gate with controls or a multiplexer may need its phase applied as one
@@ -431,8 +431,10 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         uint32_t mux_arm = 0;
         const bool is_x = g.mux < 0 && g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
                           g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.;
+        uint64_t sel_out = 0; /* lanes outside the tile whose parity picks the second matrix / factor */
         if (gate_is_diag(g)) {
-            const bool d0_is_one = (g.m[0] == 1. && g.m[1] == 0.);
+            const uint64_t lanes = gate_diag_lanes(g);
+            const bool d0_is_one = g.parity == 0 && (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
                 /* phase gate: the target acts as one more control */
                 op.kind = OP_DIAG;
@@ -443,22 +445,30 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 op.m[0] = op.m[2] = (real)g.m[6];
                 op.m[1] = op.m[3] = (real)g.m[7];
             } else {
-                op.kind = in_tile ? OP_DIAG : OP_DIAG_OUT;
+                /* d0 where an even number of the gate's lanes is 1, d1 where an odd number is: the
+                 * parity splits into a register part (regsel), a thread part (tsel) and a part
+                 * that is the same for the whole tile (sel_out) */
+                op.kind = (lanes & S) ? OP_DIAG : OP_DIAG_OUT;
                 op.m[0] = (real)g.m[0];
                 op.m[1] = (real)g.m[1];
                 op.m[2] = (real)g.m[6];
                 op.m[3] = (real)g.m[7];
-                if (in_tile) {
-                    const int j = regbit(g.target);
-                    if (j >= 0) {
-                        for (int r = 0; r < (1 << K); ++r)
-                            if (((uint32_t)r ^ flip) & (1u << j)) op.regsel |= 1u << r;
-                    } else {
-                        op.tsel = 1u << lane_to_tile[g.target];
+                uint32_t reg_bits = 0;
+                for (int lane = 0; lane < n; ++lane) {
+                    if (!((lanes >> lane) & 1ull)) continue;
+                    if (!((S >> lane) & 1ull)) {
+                        sel_out |= 1ull << lane;
+                        continue;
                     }
-                } else {
-                    op.bit = g.target;
+                    const int j = regbit(lane);
+                    if (j >= 0)
+                        reg_bits |= 1u << j;
+                    else
+                        op.tsel |= 1u << lane_to_tile[lane];
                 }
+                for (int r = 0; r < (1 << K); ++r)
+                    if (__builtin_popcount(((uint32_t)r ^ flip) & reg_bits) & 1) op.regsel |= 1u << r;
+                if (op.kind == OP_DIAG_OUT) op.bit = g.target;
             }
         } else if (is_x) {
             op.kind = OP_SWAP;
@@ -593,21 +603,24 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         } else if (op.kind == OP_SWAP) {
             op.code = OPC_SWAP(op.bit);
         } else {
+            /* regsel != 0 or a relabelled register part: the register-diagonal body (it also serves
+             * regsel == 0 after a relabelling turned every register to the same side) */
             op.code = op.regsel ? OPC_DIAG_REG : OPC_DIAG_THR;
-            /* selected factor at the same place as a multiplexed matrix: m = d0.., m1 = d1.. */
+            /* the block a thread / tile with odd parity takes: the factors exchanged, so that the
+             * selected block always starts with the factor of the registers outside regsel */
             op.m1[0] = op.m[2];
             op.m1[1] = op.m[3];
+            op.m1[2] = op.m[0];
+            op.m1[3] = op.m[1];
         }
         {
-            int sel_lane = -1;
-            if (mux_arm == ARM_MUX_OUT) sel_lane = op.mux_out;
-            if (op.kind == OP_DIAG_OUT) sel_lane = op.bit;
-            if (op.ctrl_out != 0 || sel_lane >= 0) {
+            if (mux_arm == ARM_MUX_OUT) sel_out = 1ull << op.mux_out;
+            if (op.ctrl_out != 0 || sel_out != 0) {
                 auto &ref = prog.out[prog.n_out++];
                 ref.ctrl_mask = op.ctrl_out;
+                ref.sel_mask = sel_out;
                 ref.op = (int16_t)(n_ops - 1);
-                ref.sel_lane = (int16_t)sel_lane;
-                ref.pad_ = 0;
+                ref.pad_[0] = ref.pad_[1] = ref.pad_[2] = 0;
             }
         }
         return res_kind;

@@ -66,9 +66,10 @@ struct Op {
     uint32_t arm;         /* one-hot code path selector, see ARM_* (the kernel tests bits  */
                           /* instead of switching on kind/bit: no jump table, the op loop  */
                           /* stays on the uniform datapath)                                */
-    uint32_t tsel;        /* OP_DIAG: tile-bit mask of the target when it is a thread bit  */
+    uint32_t tsel;        /* OP_DIAG: tile-bit mask of the target lanes that are thread    */
+                          /* bits: the thread takes d1 where an ODD number of them is set  */
                           /* OP_GEN + ARM_MUX_THR: tile-bit mask of the multiplexer lane   */
-    uint32_t regsel;      /* OP_DIAG: register indices whose target bit is 1               */
+    uint32_t regsel;      /* OP_DIAG: register indices with an odd number of target bits   */
                           /* OP_GEN + ARM_MUX_REG: pairs (low index) whose mux bit is 1    */
     uint64_t ctrl_out;    /* controls outside the tile, state-vector index coordinates     */
     real m1[8];           /* multiplexed OP_GEN: the matrix where the multiplexer bit is 1 */
@@ -144,9 +145,11 @@ struct PassProgram {
     int32_t n_out;
     struct OutRef {
         uint64_t ctrl_mask;   /* the op runs only in tiles whose origin has these bits set       */
+        uint64_t sel_mask;    /* the op takes m1 / d1 in tiles whose origin has an ODD number of */
+                              /* these bits set (one bit: multiplexer or diagonal target outside */
+                              /* the tile; several: a parity diagonal, Gate::parity)             */
         int16_t op;           /* op index                                                       */
-        int16_t sel_lane;     /* >= 0: the op takes m1 / d1 in tiles whose origin has this bit  */
-        int32_t pad_;
+        int16_t pad_[3];
     } out[QGB_MAX_OPS];
     Stage stage[QGB_MAX_STAGES];
     Op<real> op[QGB_MAX_OPS];
@@ -197,7 +200,14 @@ struct Gate {
      * U(t) . CX(c->t) . V(t) collapses into ONE such gate: m = U V, m1 = U X V. */
     int32_t mux = -1;
     double m1[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    /* parity diagonal (exp(i theta Z x Z x ... x Z)): with parity != 0 the gate
+     * is diagonal over ALL lanes of `parity` (target = the lowest of them): amplitudes whose index
+     * has an even number of those bits set are multiplied by (m[0], m[1]), the others by
+     * (m[6], m[7]).  An ordinary diagonal gate is the case parity == 1 << target. */
+    uint64_t parity = 0;
 };
+
+inline uint64_t gate_diag_lanes(const Gate &g) { return g.parity ? g.parity : (1ull << g.target); }
 
 inline bool gate_is_diag(const Gate &g) {
     if (g.mux >= 0) return false; /* multiplexed gates are only formed when the result is dense */

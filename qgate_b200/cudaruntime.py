@@ -67,6 +67,8 @@ def __getattr__(name):
     if name in ('initialized', 'device_ids', 'max_po2idx_per_chunk', 'memory_store_size',
                 'native_instances'):
         return getattr(_module, name)
+    if name == 'native_multi_qubit_ops':
+        return True
     raise AttributeError(name)
 
 

@@ -170,6 +170,47 @@ class NativeQubitProcessor:
     def flush(self, qstates):
         self.api.call('qgb_qproc_flush', self.ptr, qstates.ptr)
 
+    # -- "next" rows of the hot path: what the reference's front end expands
+    #    or loops over in Python, as single native calls ------------------------------------------
+    def apply_swap(self, qstates, lane_a, lane_b):
+        """Swap (model/expand.py:14-20 expands it into three CX gates): a lane relabelling."""
+        self.api.call('qgb_qproc_apply_swap', self.ptr, qstates.ptr, int(lane_a), int(lane_b))
+        states = qstates.lane_states
+        states[lane_a], states[lane_b] = states[lane_b], states[lane_a]
+
+    def apply_pauli_expi(self, theta, qstates, lanes, paulis, ctrl_lanes=()):
+        """exp(i theta P) for the Pauli string P = paulis[i] (0 I, 1 X, 2 Y, 3 Z) on lanes[i]
+        (model/expand.py:35-51 expands it into basis changes + CX chains + ExpiZ)."""
+        n, n_ctrl = len(lanes), len(ctrl_lanes)
+        self.api.call('qgb_qproc_apply_pauli_expi', self.ptr, qstates.ptr, float(theta),
+                      self.api.int_array(lanes), self.api.int_array(paulis), n,
+                      self.api.int_array(ctrl_lanes), n_ctrl)
+
+    @staticmethod
+    def pack_gates(gates):
+        """[(gate_type, adjoint, ctrl_lanes, target_lane)] -> the record array of
+        qgb_qproc_apply_gates_batch (one native call for the whole list instead of one per gate,
+        rop_executor.py:28-53)."""
+        rec = np.zeros(len(gates), _capi.GATE_OP_DTYPE)
+        for idx, (gate_type, adjoint, ctrl_lanes, target) in enumerate(gates):
+            gate_id, cargs, n_args = NativeQubitProcessor._gate_key(gate_type)
+            row = rec[idx]
+            row['gate_id'] = gate_id
+            row['adjoint'] = 1 if adjoint else 0
+            row['target'] = target
+            mask = 0
+            for lane in ctrl_lanes:
+                mask |= 1 << lane
+            row['ctrl_mask'] = mask
+            for k in range(n_args):
+                row['args'][k] = cargs[k]
+        return rec
+
+    def apply_gates_batch(self, qstates, records):
+        records = np.ascontiguousarray(records, _capi.GATE_OP_DTYPE)
+        self.api.call('qgb_qproc_apply_gates_batch', self.ptr, qstates.ptr,
+                      records.ctypes.data_as(C.c_void_p), int(records.size))
+
 
 class NativeSamplingPool:
     def __init__(self, api, ptr, qreg_ordering, mask):
@@ -288,6 +329,8 @@ class NativeQubitsStatesGetter:
 
 class RuntimeModule:
     """Module-level protocol of a runtime (cudaruntime.py:24-91), bound to one CApi."""
+
+    native_multi_qubit_ops = True    # apply_swap / apply_pauli_expi exist on the processors
 
     def __init__(self, api_factory):
         self._api_factory = api_factory

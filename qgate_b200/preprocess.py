@@ -96,6 +96,24 @@ class PauliDiagonalizer:
         return (1, 1j, -1, -1j)[self.phase_units]
 
 
+def reduce_pauli_string(gatelist):
+    """Pauli gate list (several gates per qreg allowed) -> (coefficient in {1, 1j, -1, -1j},
+    [(qreg, code)] with code 0 = I, 1 = X, 2 = Y, 3 = Z, one entry per qreg, ascending qreg id):
+    the product of the list equals coefficient x the tensor product of the coded Paulis.  Same
+    per-lane reduction as PauliDiagonalizer (pauli_gates_diagonalizer.py:96-146): a lane whose word
+    reduces to Z / X / +-Y is diagonalised by nothing / H / SH there."""
+    per_qreg = dict()
+    for gate in gatelist:
+        per_qreg.setdefault(gate.qreg, []).append(gate)
+    phase, out = 0, []
+    for qreg in sorted(per_qreg, key=lambda q: q.id):
+        lane_phase, z_based, basis = _reduce_lane(per_qreg[qreg])
+        phase += lane_phase
+        code = 0 if not z_based else 3 if basis is None else 1 if basis is gtype.H else 2
+        out.append((qreg, code))
+    return (1, 1j, -1, -1j)[phase % 4], out
+
+
 def _adjoint(gates):
     out = []
     for gate in reversed(gates):
@@ -201,6 +219,9 @@ class Preprocessor:
         if self.circ_prep not in (prefs.dynamic, prefs.static, prefs.one_static):
             raise RuntimeError('unknown circuit_prep, {}.'.format(self.circ_prep))
         self.dynamic = self.circ_prep == prefs.dynamic
+        # the runtime applies Swap and exp(i theta P) natively: they stay
+        # whole, only the grouping they imply is recorded
+        self.native_multi = bool(prefdict.get('native_multi_qubit_ops', False))
         self.reset()
 
     def reset(self):
@@ -212,6 +233,16 @@ class Preprocessor:
 
     def get_qregset(self):
         return self.groups.qregset
+
+    def _group(self, qregs, out):
+        """the qregs of one multi-qubit op must share a state vector"""
+        if len(qregs) == 1:
+            if self.groups.add(qregs[0]) and self.dynamic:
+                out.append(model.NewQreg(qregs[0]))
+            return
+        merged = self.groups.merge(qregs)
+        if merged is not None and self.dynamic:
+            out.append(model.Join(merged))
 
     def _one(self, op, out):
         groups = self.groups
@@ -244,6 +275,21 @@ class Preprocessor:
                 raise RuntimeError('unused qreg found, {}'.format(op.qreg))
             out.append(op)
         elif isinstance(op, model.Barrier):
+            out.append(op)
+        elif self.native_multi and isinstance(op, model.MultiQubitGate) and \
+                isinstance(op.gate_type, gtype.SWAP):
+            self._group(list(op.qreglist), out)
+            out.append(op)
+        elif self.native_multi and isinstance(op, model.GatelistMacro) and \
+                isinstance(op.gate_type, gtype.Expi):
+            coef, _ = reduce_pauli_string(op.gatelist)
+            if coef.imag != 0:
+                raise RuntimeError('cannot expand, {}.'.format(repr(op)))
+            qregs = []
+            for gate in op.gatelist:
+                if gate.qreg not in qregs:
+                    qregs.append(gate.qreg)
+            self._group(qregs + list(op.ctrllist or []), out)
             out.append(op)
         elif isinstance(op, (model.MultiQubitGate, model.GatelistMacro,
                              model.PauliMeasure, model.PauliProb)):

@@ -24,7 +24,7 @@ static int g_failures = 0;
 static bool g_expect_tma = false;
 static long g_warp_local = 0;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
-static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0;
+static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0, g_parity_split = 0, g_parity_gates = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
         if (!(cond)) {                        \
@@ -36,6 +36,11 @@ static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0;
 
 static void apply_direct(std::vector<cd> &amp, int n, const Gate &g) {
     const cd m00(g.m[0], g.m[1]), m01(g.m[2], g.m[3]), m10(g.m[4], g.m[5]), m11(g.m[6], g.m[7]);
+    if (g.parity) { /* d0 on an even number of set lanes, d1 on an odd number */
+        for (uint64_t i = 0; i < (1ull << n); ++i)
+            if ((i & g.ctrl_mask) == g.ctrl_mask) amp[i] *= (__builtin_popcountll(i & g.parity) & 1) ? m11 : m00;
+        return;
+    }
     const uint64_t tb = 1ull << g.target;
     for (uint64_t i = 0; i < (1ull << n); ++i) {
         if (i & tb) continue;
@@ -64,15 +69,22 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
         int expect = 0;
         for (int o = 0; o < p.n_ops; ++o) {
             const Op<real> &op = p.op[o];
-            int lane = -1;
-            if ((op.kind == OP_GEN || op.kind == OP_SHEAR) && (op.arm & ARM_MUX_OUT)) lane = op.mux_out;
-            if (op.kind == OP_DIAG_OUT) lane = op.bit;
+            const bool has_ref = expect < p.n_out && p.out[expect].op == o;
+            if ((op.kind == OP_GEN || op.kind == OP_SHEAR) && (op.arm & ARM_MUX_OUT))
+                CHECK(has_ref && p.out[expect].sel_mask == (1ull << op.mux_out), "multiplexer of op %d not referenced", o);
+            if (op.kind == OP_DIAG_OUT) CHECK(has_ref && p.out[expect].sel_mask != 0, "outside diagonal %d not referenced", o);
             if (op.kind == OP_DIAG || op.kind == OP_DIAG_OUT)
-                CHECK(op.m1[0] == op.m[2] && op.m1[1] == op.m[3], "diag op %d: d1 not mirrored into m1", o);
-            if (op.ctrl_out == 0 && lane < 0) continue;
-            CHECK(expect < p.n_out && p.out[expect].op == o && p.out[expect].ctrl_mask == op.ctrl_out &&
-                      p.out[expect].sel_lane == lane,
-                  "out-of-tile reference of op %d missing or wrong", o);
+                CHECK(op.m1[0] == op.m[2] && op.m1[1] == op.m[3] && op.m1[2] == op.m[0] && op.m1[3] == op.m[1],
+                      "diag op %d: factors not mirrored into m1", o);
+            if (op.ctrl_out != 0) CHECK(has_ref, "outside controls of op %d not referenced", o);
+            if (!has_ref) continue;
+            CHECK(p.out[expect].ctrl_mask == op.ctrl_out, "out-of-tile reference of op %d wrong", o);
+            for (int lane = 0; lane < n; ++lane)
+                if ((p.out[expect].sel_mask | p.out[expect].ctrl_mask) & (1ull << lane)) {
+                    bool in_tile = false;
+                    for (int t = 0; t < T; ++t) in_tile = in_tile || p.tile_lane[t] == lane;
+                    CHECK(!in_tile, "op %d: tile lane %d referenced as outside the tile", o, lane);
+                }
             ++expect;
         }
         CHECK(expect == p.n_out, "%d out-of-tile references, expected %d", p.n_out, expect);
@@ -176,6 +188,10 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                     const Op<real> &op = p.op[o];
                     if ((base & op.ctrl_out) != op.ctrl_out) continue;
                     CHECK((op.cmt & rmask) == 0, "thread-part controls overlap the register bits");
+                    /* parity of the lanes outside the tile that select the op's second matrix / factor */
+                    bool out_sel = false;
+                    for (int i = 0; i < p.n_out; ++i)
+                        if (p.out[i].op == o) out_sel = __builtin_popcountll(base & p.out[i].sel_mask) & 1;
                     {
                         uint32_t want = 0;
                         if (op.kind == OP_GEN || op.kind == OP_SHEAR) want = ARM_GEN(op.bit) | (op.arm & (ARM_MUX_THR | ARM_MUX_REG | ARM_MUX_OUT));
@@ -221,7 +237,7 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                             bool one = false;
                             if (op.arm & ARM_MUX_THR) one = (ebase & op.tsel) != 0;
                             if (op.arm & ARM_MUX_REG) one = (op.regsel >> r0) & 1u;
-                            if (op.arm & ARM_MUX_OUT) one = (base >> op.mux_out) & 1ull;
+                            if (op.arm & ARM_MUX_OUT) one = out_sel;
                             if (tid == 0 && r0 == 0 && bid == 0) {
                                 g_mux_thr += (op.arm & ARM_MUX_THR) != 0;
                                 g_mux_reg += (op.arm & ARM_MUX_REG) != 0;
@@ -250,7 +266,7 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                                 bool one = false;
                                 if (op.arm & ARM_MUX_THR) one = (ebase & op.tsel) != 0;
                                 if (op.arm & ARM_MUX_REG) one = (op.regsel >> r0) & 1u;
-                                if (op.arm & ARM_MUX_OUT) one = (base >> op.mux_out) & 1ull;
+                                if (op.arm & ARM_MUX_OUT) one = out_sel;
                                 if (one) {
                                     const cd n0(op.m1[0], op.m1[1]), n1(op.m1[2], op.m1[3]),
                                         n2(op.m1[4], op.m1[5]), n3(op.m1[6], op.m1[7]);
@@ -267,17 +283,13 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                         }
                     } else if (op.kind == OP_DIAG || op.kind == OP_DIAG_OUT) {
                         CHECK(op.kind == OP_DIAG || (op.tsel == 0 && op.regsel == 0), "DIAG_OUT with tile target");
-                        CHECK(op.tsel == 0 || op.regsel == 0, "diag target both thread and register bit");
                         CHECK((op.tsel & rmask) == 0, "diag thread target overlaps the register bits");
+                        if (op.tsel && op.regsel) ++g_parity_split;
                         for (int r = 0; r < (1 << K); ++r) {
                             if (!((op.regmask >> r) & 1u) || !active) continue;
-                            bool one;
-                            if (op.kind == OP_DIAG_OUT)
-                                one = (base >> op.bit) & 1ull;
-                            else if (op.regsel)
-                                one = (op.regsel >> r) & 1u;
-                            else
-                                one = (ebase & op.tsel) != 0;
+                            /* d1 where an odd number of the gate's lanes is set: register part ^
+                             * thread part ^ the part common to the tile */
+                            const bool one = (((op.regsel >> r) & 1u) != 0) ^ ((__builtin_popcount(ebase & op.tsel) & 1) != 0) ^ out_sel;
                             a[r] *= one ? m1 : m0;
                         }
                     } else {
@@ -312,7 +324,7 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
         if (lane != g.target) g.ctrl_mask |= 1ull << lane;
     }
     for (int i = 0; i < 8; ++i) g.m[i] = 0.;
-    const int kind = (int)(rng() % 6);
+    const int kind = (int)(rng() % 7);
     const double a = u(rng), b = u(rng), c = u(rng);
     switch (kind) {
     case 0: /* general unitary */
@@ -333,6 +345,18 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
     case 4: /* X */
         g.m[2] = 1.; g.m[4] = 1.;
         break;
+    case 6: { /* parity diagonal exp(i a Z x ... x Z) over 2..4 lanes, target = the lowest */
+        uint64_t lanes = 0;
+        const int want = 2 + (int)(rng() % 3);
+        for (int t = 0; t < 8 && __builtin_popcountll(lanes) < want && __builtin_popcountll(lanes) < n; ++t) lanes |= 1ull << (rng() % n);
+        g.parity = lanes;
+        g.target = __builtin_ctzll(lanes);
+        g.ctrl_mask &= ~lanes;
+        g.m[0] = std::cos(a); g.m[1] = std::sin(a);
+        g.m[6] = std::cos(a); g.m[7] = -std::sin(a);
+        ++g_parity_gates;
+        break;
+    }
     case 5: /* Y-like anti-diagonal */
         g.m[2] = std::cos(a); g.m[3] = std::sin(a);
         g.m[4] = std::cos(b); g.m[5] = std::sin(b);
@@ -459,6 +483,11 @@ int main() {
     }
     std::printf("shear ops %ld, direct 2x2 ops %ld, stages stored through a relabelling %ld, residual phase ops %ld\n",
                 g_shear, g_direct, g_flipped_stages, g_residual_ops);
+    std::printf("parity diagonals %ld, of which split over register and thread bits in a stage %ld\n", g_parity_gates, g_parity_split);
+    if (g_parity_gates == 0 || g_parity_split == 0) {
+        std::printf("FAIL: parity diagonals were never exercised\n");
+        return 1;
+    }
     if (g_shear == 0 || g_direct == 0 || g_flipped_stages == 0 || g_residual_ops == 0) {
         std::printf("FAIL: a shear path was never exercised\n");
         return 1;
