@@ -271,7 +271,14 @@ int qgb_stats_reset(void);
  *                               changes (1-qubit gates, merged into their neighbours) around ONE
  *                               parity-phase diagonal op of the fused pass.
  * f-1  batch submit (model_executor.py:80-175 + rop_executor.py:28-53 make one native call per
- *      gate): qgb_qproc_apply_gates_batch queues n_ops gates in one call. */
+ *      gate): qgb_qproc_apply_gates_batch queues n_ops gates in one call.
+ * f-2  Simulator.sample (simulator.py:85-119 re-runs the circuit once per shot): for circuits whose
+ *      measurements are all at the end, qgb_pool_sample_sequential answers n_shots shots from ONE
+ *      pool over the measured qubits — pool lane n_lanes-1 = the first measured qubit ... lane 0 = the
+ *      last; randnum[s * n_lanes + k] is the draw of shot s for its k-th Measure, consumed exactly
+ *      as the reference's Measure ops consume np.random (model_executor.py:117-122); obs[s] = the pool
+ *      index of the outcome (no empty-lane deposit). */
+int qgb_pool_sample_sequential(qgb_handle pool, int64_t *obs, int n_shots, const double *randnum);
 int qgb_qproc_apply_swap(qgb_handle qproc, qgb_handle qstates, int lane_a, int lane_b);
 int qgb_qproc_apply_pauli_expi(qgb_handle qproc, qgb_handle qstates, double theta, const int *lanes,
                                const int *paulis, int n, const int *ctrl_lanes, int n_ctrl);

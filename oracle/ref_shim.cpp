@@ -515,6 +515,10 @@ int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *
     QGB_CATCH
 }
 
+int qgb_pool_sample_sequential(qgb_handle, int64_t *, int, const double *) {
+    return fail(QGB_ERR_RUNTIME, "the reference pool has no sequential sampler (its front end re-runs the circuit per shot).");
+}
+
 int qgb_pool_delete(qgb_handle pool) {
     QGB_TRY
     delete SP(pool);

@@ -76,6 +76,7 @@ SIGNATURES = {
     'qgb_getter_create_sampling_pool': [_h, _ip, _ip, _hp, _i, _i, _i, _ip, _i, _hp],
     'qgb_pool_sample': [_h, _i64p, _i, _dp],
     'qgb_pool_delete': [_h],
+    'qgb_pool_sample_sequential': [_h, _i64p, _i, _dp],
     'qgb_stats_get': [C.POINTER(Stats)],
     'qgb_stats_reset': [],
     'qgb_qproc_flush': [_h, _h],

@@ -1621,6 +1621,31 @@ int qgb_pool_sample(qgb_handle pool, int64_t *obs, int n_samples, const double *
     QGB_CATCH
 }
 
+int qgb_pool_sample_sequential(qgb_handle pool, int64_t *obs, int n_shots, const double *randnum) {
+    QGB_TRY
+    Pool *p = SP(pool);
+    require_init();
+    if (!p->d_cum || !p->finalized) fail(QGB_ERR_RUNTIME, "sampling pool is not ready.");
+    if (n_shots < 0) fail(QGB_ERR_INVALID, "negative number of shots.");
+    if (n_shots == 0 || p->n_lanes == 0) {
+        for (int i = 0; i < n_shots; ++i) obs[i] = 0;
+        return QGB_OK;
+    }
+    const size_t n_rand = (size_t)n_shots * (size_t)p->n_lanes;
+    char *d_buf = static_cast<char *>(g.pool.alloc(n_rand * 8 + (size_t)n_shots * 8));
+    double *d_rand = reinterpret_cast<double *>(d_buf);
+    int64_t *d_obs = reinterpret_cast<int64_t *>(d_buf + n_rand * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_rand, randnum, n_rand * 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_CHECK(launch_sample_sequential(p->d_cum, p->n_lanes, d_rand, d_obs, n_shots, g.stream));
+    CUDA_CHECK(cudaMemcpyAsync(obs, d_obs, (size_t)n_shots * 8, cudaMemcpyDeviceToHost, g.stream));
+    stream_sync();
+    g.pool.release(d_buf);
+    g.stats.kernel_launches += 1;
+    g.stats.h2d_bytes += (int64_t)n_rand * 8;
+    g.stats.d2h_bytes += (int64_t)n_shots * 8;
+    QGB_CATCH
+}
+
 int qgb_pool_delete(qgb_handle pool) {
     QGB_TRY
     pool_destroy(SP(pool));

@@ -124,6 +124,11 @@ cudaError_t launch_scan_phase3(int prec, const void *amp, double *d_cum, int64_t
 cudaError_t launch_sample(int prec, const double *d_cum, int n_lanes, const double *d_rand,
                           int64_t *d_obs, int n_samples, SortedBits empty_lanes, cudaStream_t stream);
 
+/* obs[s] = outcome of n_bits sequential measurements (most significant pool lane first) decided by
+ * the draws rnd[s * n_bits + k] against conditional probabilities taken from the cumulative array */
+cudaError_t launch_sample_sequential(const double *d_cum, int n_bits, const double *d_rand, int64_t *d_obs,
+                                     int n_shots, cudaStream_t stream);
+
 /* ---- sharded states: lane exchange over peer memory (dist.cu) --------------------------- */
 #define QGB_MAX_EXCHANGE_LANES 4
 

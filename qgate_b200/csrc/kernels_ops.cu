@@ -537,6 +537,30 @@ sample_kernel(const double *__restrict__ cum, int64_t n_states, const double *__
     obs[i] = (int64_t)v;
 }
 
+/* ---- Simulator.sample for terminal measurements (simulator.py:85-119) ------
+ * The reference re-runs the whole circuit per shot; its Measure ops draw one uniform number each and
+ * answer 0 if r < P(qubit = 0 | earlier outcomes of the shot).  With all measurements at the end,
+ * those conditional probabilities are ratios of partial sums of ONE marginal distribution, i.e.
+ * differences of the pool's cumulative array: shot s walks the binary tree over the n_bits pool
+ * lanes from the most significant one (the first measured qubit) down, one draw per level. */
+__global__ void __launch_bounds__(256)
+sample_sequential_kernel(const double *__restrict__ cum, int n_bits, const double *__restrict__ rnd,
+                         int64_t *__restrict__ obs, int n_shots) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_shots) return;
+    const double *r = rnd + (int64_t)s * n_bits;
+    int64_t prefix = 0;
+    for (int k = 0; k < n_bits; ++k) {
+        const int rest = n_bits - k; /* undecided lanes */
+        const int64_t lo = prefix << rest, mid = lo + ((int64_t)1 << (rest - 1)), hi = lo + ((int64_t)1 << rest);
+        const double c_lo = lo ? cum[lo - 1] : 0., c_mid = cum[mid - 1], c_hi = cum[hi - 1];
+        const double all = c_hi - c_lo;
+        const double p0 = all > 0. ? (c_mid - c_lo) / all : 1.;
+        prefix = (prefix << 1) | (r[k] < p0 ? 0 : 1);
+    }
+    obs[s] = prefix;
+}
+
 inline unsigned grid_for(uint64_t n, unsigned nthr, unsigned cap) {
     uint64_t b = (n + nthr - 1) / nthr;
     if (b < 1) b = 1;
@@ -799,6 +823,13 @@ cudaError_t launch_scan_phase3(int prec, const void *amp, double *d_cum, int64_t
     else
         scan_phase3_kernel<SrcAmp<float>><<<nblocks, SCAN_THREADS, 0, stream>>>(
             SrcAmp<float>{reinterpret_cast<const float2 *>(amp)}, d_cum, n, d_block_sums, global_offset, norm);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample_sequential(const double *d_cum, int n_bits, const double *d_rand, int64_t *d_obs,
+                                     int n_shots, cudaStream_t stream) {
+    if (n_shots <= 0) return cudaSuccess;
+    sample_sequential_kernel<<<(unsigned)((n_shots + 255) / 256), 256, 0, stream>>>(d_cum, n_bits, d_rand, d_obs, n_shots);
     return cudaGetLastError();
 }
 

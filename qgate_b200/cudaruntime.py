@@ -67,7 +67,7 @@ def __getattr__(name):
     if name in ('initialized', 'device_ids', 'max_po2idx_per_chunk', 'memory_store_size',
                 'native_instances'):
         return getattr(_module, name)
-    if name == 'native_multi_qubit_ops':
+    if name in ('native_multi_qubit_ops', 'native_sample'):
         return True
     raise AttributeError(name)
 

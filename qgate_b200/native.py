@@ -242,6 +242,17 @@ class NativeSamplingPool:
                       randnum.ctypes.data_as(C.POINTER(C.c_double)))
         return ObservationList(self.qreg_ordering, obs, self.mask)
 
+    def sample_sequential(self, n_shots, randnum):
+        """n_shots shots of sequential measurements of the pool's qregs, the LAST qreg of the
+        ordering measured first; randnum[s, k] decides the k-th measurement of shot s exactly as
+        the reference's Measure op would (0 if r < P(0 | earlier outcomes), model_executor.py:
+        117-122).  Returns the pool indices (int64[n_shots]); SURVEY section 8f-2."""
+        randnum = np.ascontiguousarray(randnum, np.float64)
+        obs = np.empty([n_shots], np.int64)
+        self.api.call('qgb_pool_sample_sequential', self.ptr, obs.ctypes.data_as(C.POINTER(C.c_int64)),
+                      int(n_shots), randnum.ctypes.data_as(C.POINTER(C.c_double)))
+        return obs
+
 
 class NativeQubitsStatesGetter:
     def __init__(self, api, dtype, ptr):
@@ -331,6 +342,10 @@ class RuntimeModule:
     """Module-level protocol of a runtime (cudaruntime.py:24-91), bound to one CApi."""
 
     native_multi_qubit_ops = True    # apply_swap / apply_pauli_expi exist on the processors
+
+    @property
+    def native_sample(self):           # pools answer Simulator.sample for terminal measurements
+        return self.api.backend_name.startswith('cuda')
 
     def __init__(self, api_factory):
         self._api_factory = api_factory

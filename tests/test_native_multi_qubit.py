@@ -163,3 +163,63 @@ def test_sampling_pool_and_readout_follow_relabelled_lanes(cuda_runtime, ref_run
     assert np.abs(outs[0][1] - outs[1][1]).max() < 1e-12
     assert np.array_equal(outs[0][2], outs[1][2])
     assert np.array_equal(outs[0][3], outs[1][3])
+
+
+# ---- f-2: Simulator.sample without the per-shot re-run ------------------------------------------
+
+def _terminal_circuit(n=10):
+    q, ops = circuits.random_u3_cx(S, n, 5, seed=31)
+    fresh = S.new_qreg()                       # never touched by a gate: measured as |0>, still one draw
+    refs = S.new_references(7)
+    order = [q[4], q[0], fresh, q[9], q[3], q[7], q[5]]
+    ops = ops + [S.measure(r, x) for r, x in zip(refs, order)]
+    return ops, refs
+
+
+def test_terminal_measurement_detection():
+    from qgate_b200.simulator.simulator import Simulator
+    from qgate_b200 import model
+    from qgate_b200.preprocess import Preprocessor
+    ops, refs = _terminal_circuit()
+    flat = Preprocessor(circuit_prep='dynamic').preprocess(model.GateList(ops))
+    prefix, measures = Simulator._terminal_measurements(flat)
+    assert len(measures) == 7 and not any(isinstance(op, model.Measure) for op in prefix)
+    q = S.new_qregs(2)
+    r = S.new_references(2)
+    mid = [S.H(q[0]), S.measure(r[0], q[0]), S.H(q[1]), S.measure(r[1], q[1])]
+    assert Simulator._terminal_measurements(Preprocessor().preprocess(model.GateList(mid))) is None
+    cond = [S.H(q[0]), S.measure(r[0], q[0]), S.if_(r[0], 1, S.X(q[1])), S.measure(r[1], q[1])]
+    assert Simulator._terminal_measurements(Preprocessor().preprocess(model.GateList(cond))) is None
+    twice = [S.H(q[0]), S.measure(r[0], q[0]), S.measure(r[1], q[0])]
+    assert Simulator._terminal_measurements(Preprocessor().preprocess(model.GateList(twice))) is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prep', ('dynamic', 'one_static'))
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_native_sample_matches_the_per_shot_loop_shot_for_shot(cuda_runtime, ref_runtime, dtype, prep):
+    """4000 shots from ONE run + one pool on the engine = the reference CPU runtime re-running the
+    circuit 4000 times (simulator.py:85-119) under the same seed, observation for observation."""
+    ops, refs = _terminal_circuit()
+    ref_order = [refs[3], refs[0], refs[6], refs[2], refs[5]]            # a subset, reordered
+    sim = with_runtime(cuda_runtime, dtype=dtype, circuit_prep=prep)
+    api = cuda_runtime.get_api()
+    api.stats_reset()
+    np.random.seed(99)
+    got = sim.sample(ops, ref_order, 4000).intarray
+    launches = api.stats()['kernel_launches']
+    after = np.random.random_sample()           # the global RNG stream stands where the loop leaves it
+    sim.terminate()
+    loop = with_runtime(ref_runtime.module, dtype=dtype, circuit_prep=prep)
+    np.random.seed(99)
+    want = loop.sample(ops, ref_order, 4000).intarray
+    assert after == np.random.random_sample()
+    loop.terminate()
+    assert np.array_equal(got, want)
+    assert len(set(got.tolist())) > 8
+    assert launches < 400, launches              # not 4000 re-runs
+    # and the engine's own per-shot loop (the fallback for mid-circuit measurements) agrees too
+    sim = with_runtime(cuda_runtime, dtype=dtype, circuit_prep=prep, native_sample=False)
+    np.random.seed(99)
+    assert np.array_equal(sim.sample(ops, ref_order, 300).intarray, want[:300])
+    sim.terminate()
