@@ -255,6 +255,8 @@ typedef struct qgb_stats {
     int64_t direct_ops;           /* dense 2x2 gates applied as a direct 2x2 product   */
     int64_t native_swaps;         /* qgb_qproc_apply_swap calls (lane relabellings)     */
     int64_t native_pauli_exps;    /* qgb_qproc_apply_pauli_expi calls                  */
+    int64_t fan_ops;              /* phase fans applied (controlled phases sharing a lane, */
+                                  /* merged into one op: a QFT's n(n-1)/2 become n)         */
 } qgb_stats;
 int qgb_stats_get(qgb_stats *out);
 int qgb_stats_reset(void);

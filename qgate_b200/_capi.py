@@ -38,7 +38,7 @@ class Stats(C.Structure):
     _fields_ = [(name, C.c_int64) for name in (
         'kernel_launches', 'gates_submitted', 'gates_executed', 'tile_passes',
         'gate_amp_updates', 'pass_bytes', 'h2d_bytes', 'd2h_bytes', 'tma_passes', 'shear_ops',
-        'direct_ops', 'native_swaps', 'native_pauli_exps')]
+        'direct_ops', 'native_swaps', 'native_pauli_exps', 'fan_ops')]
 
     def as_dict(self):
         return {name: int(getattr(self, name)) for name, _ in self._fields_}

@@ -213,6 +213,7 @@ struct Pool {
 struct Options {
     int64_t fuse = 1;
     int64_t merge = 1;
+    int64_t fans = 1; /* controlled phases that share a lane merge into one phase fan (program.h OP_FAN) */
     /* 1: every gate as submitted, one kernel each, in the reference CPU runtime's arithmetic
      * operation by operation (CPUQubitProcessor.cpp:316-324): amplitudes bit-identical to
      * qgate.simulator.cpu's.  A verification mode (one state sweep per gate), off by default. */
@@ -346,7 +347,7 @@ void flush_tiled(QStates *qs) {
     /* ops per pass: their matrices are staged in shared memory, their predicates are one bit each */
     const int max_ops = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.max_gates_per_pass, 32));
     /* smem limit: shrink the tile until it fits the device's opt-in shared memory */
-    while (cfg.T > cfg.K + 5 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, 8, n_buf, max_ops) > (size_t)g.max_smem_optin)
+    while (cfg.T > cfg.K + 5 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, 8, n_buf, max_ops, QGB_MAX_FANS) > (size_t)g.max_smem_optin)
         --cfg.T;
     cfg.T = std::min(cfg.T, qs->n_lanes);
     cfg.L = std::max(fp32 ? 1 : 0, std::min(cfg.L, cfg.T - 1));
@@ -366,7 +367,7 @@ void flush_tiled(QStates *qs) {
         if (g.opt.ctas_per_sm > 0) want_ctas = (int)g.opt.ctas_per_sm;
         const size_t budget = (size_t)(g.max_smem_optin + 1024) / want_ctas - 1024;
         int ms = QGB_MAX_STAGES;
-        while (ms > 2 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, ms, n_buf, max_ops) > budget) --ms;
+        while (ms > 2 && tma_pass_smem_bytes(qs->prec, cfg.T, cfg.K, ms, n_buf, max_ops, QGB_MAX_FANS) > budget) --ms;
         cfg.max_stages = ms;
     }
     cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : default_max_cost(fp32, cfg.shear);
@@ -386,6 +387,7 @@ void flush_tiled(QStates *qs) {
         g.stats.pass_bytes += (int64_t)(2 * qs->bytes());
         g.stats.shear_ops += st.shear_ops;
         g.stats.direct_ops += st.direct_ops;
+        g.stats.fan_ops += st.fan_ops;
     }
 }
 
@@ -400,6 +402,17 @@ void flush(QStates *qs) {
             flush_tiled<float>(qs);
     } else {
         for (const Gate &gt : qs->queue) {
+            if (!gt.fan.empty()) {
+                /* a phase fan (formed while the tiled path was on): its controlled phases one by one */
+                for (const Gate::FanTerm &t : gt.fan) {
+                    const double cp[8] = {1., 0., 0., 0., 0., 0., t.re, t.im};
+                    CUDA_CHECK(launch_simple_gate(qs->prec, qs->d_amp, qs->n_lanes, cp, t.lane, 1ull << gt.target, 0,
+                                                  false, g.stream));
+                    g.stats.kernel_launches += 1;
+                }
+                g.stats.gates_executed += 1;
+                continue;
+            }
             if (gt.parity) {
                 CUDA_CHECK(launch_simple_parity(qs->prec, qs->d_amp, qs->n_lanes, gt.m, gt.m + 6, gt.parity,
                                                 gt.ctrl_mask, g.stream));
@@ -447,7 +460,7 @@ void submit_gate(QStates *qs, const double *mat8, const int *ctrl, int n_ctrl, i
 void submit_queued(QStates *qs, const Gate &gt, int n_ctrl) {
     /* merging pays on the tiled path only; the one-kernel-per-gate path keeps the submitted gates */
     const bool tiled = !g.opt.exact && g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec);
-    enqueue_gate(qs->queue, gt, g.opt.merge != 0 && tiled);
+    enqueue_gate(qs->queue, gt, g.opt.merge != 0 && tiled, g.opt.fans != 0);
     g.stats.gates_submitted += 1;
     g.stats.gate_amp_updates += (int64_t)1 << (qs->n_lanes - n_ctrl);
     if ((int64_t)qs->queue.size() >= g.opt.queue_limit) flush(qs);
@@ -1670,6 +1683,7 @@ int qgb_set_option(const char *name, int64_t value) {
     const std::string k(name ? name : "");
     if (k == "fuse") g.opt.fuse = value;
     else if (k == "merge") g.opt.merge = value;
+    else if (k == "fans") g.opt.fans = value;
     else if (k == "exact") g.opt.exact = value;
     else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
     else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;

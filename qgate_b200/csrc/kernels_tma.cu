@@ -480,6 +480,12 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
     const uint32_t tid = threadIdx.x;
     const uint32_t nthr = WS ? blockDim.x - 32u : blockDim.x; /* computing threads == 2^(T-K) */
     const bool producer = WS && tid >= nthr;
+    /* phase fans (OP_FAN): per fan two tables of thread factors — one indexed by the low FLO bits of
+     * the thread number, one by the rest — and the factor of the tile being worked on / the next one */
+    const int FLO = (T - K + 1) >> 1, FHI = T - K - FLO;
+    const int fan_tab_size = (1 << FLO) + (1 << FHI);
+    cplx *fan_tab = reinterpret_cast<cplx *>(lut + (size_t)prog.n_stages * nthr); /* (a multiple of 128 bytes in) */
+    cplx *fan_out = fan_tab + prog.n_fans * fan_tab_size;                        /* [2][n_fans] */
 
     /* the pass's matrices, once per CTA */
     for (int i = tid; !producer && i < 2 * MS * prog.n_ops; i += nthr) {
@@ -510,6 +516,49 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             if (__popc(ebase & op.tsel) & 1) sel_thr |= 1u << o; /* one bit, or the parity of several */
         }
     }
+    const uint64_t n_tiles = 1ull << (prog.n_lanes - T);
+    const uint64_t stride = gridDim.x;
+    /* state-vector index of the origin of tile number t */
+    auto tile_base = [&](uint64_t t) {
+        uint64_t base = 0;
+#pragma unroll
+        for (int d = 0; d < QGB_MAX_GROUPS; ++d)
+            base |= (uint64_t)(((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.base_shift[d];
+        return base;
+    };
+    /* fan f's factor for the tile at `base`: the product of its outside-the-tile terms whose lane is 1
+     * (in double, rounded once) */
+    auto fan_tile_factor = [&](int f, uint64_t base) {
+        const auto &fn = prog.fan[f];
+        double pr = 1., pi = 0.;
+        for (int k = fn.first + fn.n_thr; k < fn.first + fn.n_thr + fn.n_out; ++k) {
+            const auto &tm = prog.fan_term[k];
+            if ((base >> tm.bit) & 1ull) {
+                const double r = pr * tm.re - pi * tm.im;
+                pi = pr * tm.im + pi * tm.re;
+                pr = r;
+            }
+        }
+        cplx out;
+        out.x = (real)pr, out.y = (real)pi;
+        return out;
+    };
+    for (int i = tid; !producer && i < prog.n_fans * fan_tab_size; i += nthr) {
+        const int f = i / fan_tab_size, e = i - f * fan_tab_size;
+        const uint32_t x = e < (1 << FLO) ? (uint32_t)e : ((uint32_t)(e - (1 << FLO)) << FLO); /* thread-number bits */
+        const auto &fn = prog.fan[f];
+        double pr = 1., pi = 0.;
+        for (int k = fn.first; k < fn.first + fn.n_thr; ++k) {
+            const auto &tm = prog.fan_term[k];
+            if ((x >> tm.bit) & 1u) {
+                const double r = pr * tm.re - pi * tm.im;
+                pi = pr * tm.im + pi * tm.re;
+                pr = r;
+            }
+        }
+        fan_tab[i].x = (real)pr, fan_tab[i].y = (real)pi;
+    }
+    if (!producer && (int)tid < prog.n_fans && blockIdx.x < n_tiles) fan_out[tid] = fan_tile_factor((int)tid, tile_base(blockIdx.x));
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) {
@@ -519,9 +568,6 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
-
-    const uint64_t n_tiles = 1ull << (prog.n_lanes - T);
-    const uint64_t stride = gridDim.x;
 
     /* tile number -> tensor coordinates of the tile's origin */
     auto issue_load = [&](uint64_t t, int b) {
@@ -578,6 +624,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
 
     int b = 0;            /* buffer of the tile being worked on */
     uint32_t parity = 0;  /* phase of full[b] this tile completes */
+    int fan_cur = 0;      /* half of fan_out that holds this tile's factors */
 #ifdef QGB_PHASE_TIMING
     long long ph_wait = 0, ph_load = 0, ph_ops = 0, ph_store = 0, ph_tail = 0, ph_t;
 #define PH_MARK(acc) do { const long long now_ = clock64(); acc += now_ - ph_t; ph_t = now_; } while (0)
@@ -600,10 +647,11 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         /* index of the tile's origin -> the ops this tile skips (controls outside the tile) and
          * the ops that take their second matrix / factor (multiplexer or diagonal target
          * outside the tile): CTA-uniform bit masks over the ops */
-        uint64_t base = 0;
-#pragma unroll
-        for (int d = 0; d < QGB_MAX_GROUPS; ++d)
-            base |= (uint64_t)(((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.base_shift[d];
+        const uint64_t base = tile_base(t);
+        /* the fans' factors of the NEXT tile, one thread per fan: published by the barrier that ends
+         * this tile (the buffer written here was last read in the previous tile) */
+        if ((int)tid < prog.n_fans && t + stride < n_tiles)
+            fan_out[(fan_cur ^ 1) * prog.n_fans + tid] = fan_tile_factor((int)tid, tile_base(t + stride));
         uint32_t eff = act, sel = sel_thr;
         for (int i = 0; i < prog.n_out; ++i) {
             const uint64_t cm = prog.out[i].ctrl_mask;
@@ -640,10 +688,24 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
                     if (!(eff & bit)) continue;
                     const Op<real> &op = prog.op[o];
                     const real *mm = mo + ((sel & bit) ? MS : 0);
-                    if (op.code >= OPC_SHEAR(0))
+                    if (op.code >= OPC_SHEAR(0)) {
                         lean_apply_shear<real, K>(a, op, mo, mm);
-                    else
+                    } else if (op.code == OPC_FAN) {
+                        /* one factor per thread and tile on the registers the hub predicate admits, then
+                         * one phase per term whose lane is a register bit of this stage */
+                        const auto &fn = prog.fan[op.bit];
+                        const cplx *tab = fan_tab + op.bit * fan_tab_size;
+                        const cplx f0 = tab[tid & ((1u << FLO) - 1u)], f1 = tab[(1 << FLO) + (tid >> FLO)];
+                        const cplx f2 = fan_out[fan_cur * prog.n_fans + op.bit];
+                        const real gr = f0.x * f1.x - f0.y * f1.y, gi = f0.x * f1.y + f0.y * f1.x;
+                        lean_phase<K>(a, gr * f2.x - gi * f2.y, gr * f2.y + gi * f2.x, op.regmask);
+                        for (int k = 0; k < fn.n_reg; ++k) {
+                            const auto &tm = prog.fan_term[fn.first + fn.n_thr + fn.n_out + k];
+                            lean_phase<K>(a, (real)tm.re, (real)tm.im, (uint32_t)fn.reg_mask[k]);
+                        }
+                    } else {
                         lean_apply_op<real, K, DIRECT>(a, op, mo, mm);
+                    }
                 }
             }
 
@@ -677,6 +739,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             b = 0;
             parity ^= 1u;
         }
+        fan_cur ^= 1;
     }
     if (!WS && tid == 0) bulk_wait_read<0>();
 #ifdef QGB_PHASE_TIMING
@@ -798,7 +861,7 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
     TmaGeometry geo;
     rc = encode_map<real>(prog, amp, &map, &geo);
     if (rc != cudaSuccess) return rc;
-    const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.K, prog.n_stages, n_buf, prog.n_ops);
+    const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.K, prog.n_stages, n_buf, prog.n_ops, prog.n_fans);
     const int nthr = 1 << (prog.T - prog.K);
     (void)min_ctas;
     if (!g_tma_ws) { /* A/B switch: the unspecialised kernel for every shape */
@@ -826,12 +889,15 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
 
 } // namespace
 
-size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops) {
+size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops, int n_fans) {
     const size_t elem = prec == 1 ? 16 : 8;
     size_t tiles = n_buf * (elem << T);
     tiles = (tiles + 1023) & ~(size_t)1023;
+    /* phase fans: two tables of thread factors and two tile factors each */
+    const int flo = (T - K + 1) >> 1, fhi = T - K - flo;
+    const size_t fans = (size_t)n_fans * elem * ((size_t)(1 << flo) + (size_t)(1 << fhi) + 2);
     /* + mbarriers, the matrices of up to QGB_MAX_OPS ops, the per-stage thread table, alignment slack */
-    return tiles + 16 * n_buf + (prec == 1 ? 128 : 96) * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + 1024;
+    return tiles + 16 * n_buf + (prec == 1 ? 128 : 96) * (size_t)n_ops + sizeof(uint32_t) * ((size_t)n_stages << (T - K)) + fans + 1024;
 }
 
 void tma_pass_set_warp_specialised(int on) { g_tma_ws = on ? 1 : 0; }

@@ -90,14 +90,77 @@ namespace {
 
 inline bool mat_is_diag(const double *m) { return m[2] == 0. && m[3] == 0. && m[4] == 0. && m[5] == 0.; }
 
+const double kIdentity[8] = {1., 0., 0., 0., 0., 0., 1., 0.};
+
 inline uint64_t touched_lanes(const Gate &p) {
-    return p.ctrl_mask | (1ull << p.target) | (p.mux >= 0 ? (1ull << p.mux) : 0ull) | p.parity;
+    return p.ctrl_mask | (1ull << p.target) | (p.mux >= 0 ? (1ull << p.mux) : 0ull) | p.parity | gate_fan_lanes(p);
+}
+
+/* a controlled phase CP(a, b; e^{i phi}): diag(1, e^{i phi}) on the target under ONE control, which is
+ * symmetric in its two lanes */
+inline bool is_controlled_phase(const Gate &p) {
+    return p.fan.empty() && p.mux < 0 && p.parity == 0 && popcount64(p.ctrl_mask) == 1 && mat_is_diag(p.m) &&
+           p.m[0] == 1. && p.m[1] == 0.;
+}
+
+const int kMaxFanTerms = 48;
+
+void fan_add_term(Gate &fan, int lane, double re, double im) {
+    for (Gate::FanTerm &t : fan.fan)
+        if (t.lane == lane) {
+            const double r = t.re * re - t.im * im, i = t.re * im + t.im * re;
+            t.re = r, t.im = i;
+            return;
+        }
+    fan.fan.push_back({lane, re, im});
+}
+
+/* Phase fans: the controlled phase g = CP(a, b) moves backwards over the queued gates it commutes
+ * with (everything that acts diagonally on a and on b) until it meets a fan whose hub is a or b (it
+ * becomes one more term), or another controlled phase that shares a lane with it (the two become a
+ * fan with that lane as the hub).  The n - 1 - i controlled phases a QFT applies onto qubit i end up
+ * as ONE gate, whatever order the circuit lists them in. */
+bool merge_into_fan(std::vector<Gate> &queue, const Gate &g) {
+    const int a = __builtin_ctzll(g.ctrl_mask), b = g.target;
+    const uint64_t ab = (1ull << a) | (1ull << b);
+    const int lo = std::max(0, (int)queue.size() - 256);
+    for (int i = (int)queue.size() - 1; i >= lo; --i) {
+        Gate &p = queue[i];
+        if (!p.fan.empty()) {
+            if ((p.target == a || p.target == b) && p.ctrl_mask == 0 && (int)p.fan.size() < kMaxFanTerms) {
+                fan_add_term(p, p.target == a ? b : a, g.m[6], g.m[7]);
+                return true;
+            }
+            continue; /* diagonal: commutes */
+        }
+        if (is_controlled_phase(p)) {
+            const int pa = __builtin_ctzll(p.ctrl_mask), pb = p.target;
+            const uint64_t pab = (1ull << pa) | (1ull << pb);
+            if (pab == ab) { /* the same pair: the phases multiply */
+                const double r = p.m[6] * g.m[6] - p.m[7] * g.m[7], im = p.m[6] * g.m[7] + p.m[7] * g.m[6];
+                p.m[6] = r, p.m[7] = im;
+                return true;
+            }
+            if (pab & ab) {
+                const int hub = __builtin_ctzll(pab & ab);
+                Gate f;
+                std::memcpy(f.m, kIdentity, sizeof(f.m));
+                f.target = hub;
+                f.ctrl_mask = 0;
+                f.fan.push_back({pa == hub ? pb : pa, p.m[6], p.m[7]});
+                f.fan.push_back({a == hub ? b : a, g.m[6], g.m[7]});
+                p = f;
+                return true;
+            }
+            continue;
+        }
+        if ((p.target == a || p.target == b) && !gate_is_diag(p)) return false; /* does not commute */
+    }
+    return false;
 }
 
 /* does p act non-diagonally on `lane`?  (a control / multiplexer lane is acted on diagonally) */
 inline bool acts_nondiag_on(const Gate &p, int lane) { return p.target == lane && !gate_is_diag(p); }
-
-const double kIdentity[8] = {1., 0., 0., 0., 0., 0., 1., 0.};
 
 typedef std::complex<double> cd;
 
@@ -142,8 +205,9 @@ bool shear_factor(const double *m, int s, ShearCoef &out) {
  *                              by c: m1 = g.m p.m) or into a p already multiplexed by c, provided
  *                              the result is dense (diagonal controlled gates stay cheap phases);
  *   anything else:             folds only into an identical-signature gate directly before it. */
-bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
-    if (merge && !queue.empty() && g.mux < 0 && g.parity == 0) {
+bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge, bool fans) {
+    if (merge && fans && !queue.empty() && is_controlled_phase(g) && merge_into_fan(queue, g)) return true;
+    if (merge && !queue.empty() && g.mux < 0 && g.parity == 0 && g.fan.empty()) {
         const int n_ctrl = popcount64(g.ctrl_mask);
         if (n_ctrl <= 1) {
             const uint64_t tm = 1ull << g.target;
@@ -154,6 +218,11 @@ bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
                 if (!(touched_lanes(p) & tm)) {
                     if (c >= 0 && acts_nondiag_on(p, c)) break; /* g does not commute with p */
                     continue;
+                }
+                if (!p.fan.empty()) {
+                    /* a fan acts diagonally on all its lanes: a diagonal g commutes with it */
+                    if (mat_is_diag(g.m)) continue;
+                    break;
                 }
                 if (p.target != g.target || p.parity) break;
                 if (c < 0) {
@@ -179,7 +248,7 @@ bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge) {
             }
         } else {
             Gate &p = queue.back();
-            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask && p.mux < 0 && p.parity == 0) {
+            if (p.target == g.target && p.ctrl_mask == g.ctrl_mask && p.mux < 0 && p.parity == 0 && p.fan.empty()) {
                 matmul2(g.m, p.m, p.m);
                 return true;
             }
@@ -214,7 +283,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
     std::vector<uint64_t> stageR; /* lane masks of the register bits of each stage */
     std::vector<uint64_t> stageMux; /* multiplexer lanes of the gates of each stage */
     int first_block = -1;
-    int cost = 0, slots = 0;
+    int cost = 0, slots = 0, n_fans = 0, n_fan_terms = 0;
 
     for (int i = 0; i < (int)queue.size(); ++i) {
         if (first_block >= 0 && i - first_block > cfg.lookahead) break;
@@ -224,11 +293,15 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         const uint64_t xq = diag ? 0 : tm;
         const uint64_t zq = g.ctrl_mask | (diag ? gate_diag_lanes(g) : 0) | (g.mux >= 0 ? (1ull << g.mux) : 0ull);
         bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
-        const int gcost = diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4));
+        const bool is_fan = !g.fan.empty();
+        /* (a fan multiplies half of the amplitudes once and builds one factor per thread and tile) */
+        const int gcost = is_fan ? 2 : (diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4)));
         /* op slots: a sheared gate with controls or a multiplexer may need its phase applied as one
          * more (diagonal) op of this pass */
         const int gslots = (cfg.shear && !diag && (g.mux >= 0 || g.ctrl_mask != 0)) ? 2 : 1;
         if (!blocked && !picked.empty() && (slots + gslots > max_ops || cost + gcost > cfg.max_cost))
+            blocked = true;
+        if (!blocked && is_fan && (n_fans + 1 > QGB_MAX_FANS || n_fan_terms + (int)g.fan.size() > QGB_MAX_FAN_TERMS))
             blocked = true;
         bool add_lane = false;
         if (!blocked && xq && !(S & xq)) {
@@ -268,6 +341,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         picked.push_back({i, (int)stageR.size() - 1});
         cost += gcost;
         slots += gslots;
+        if (is_fan) ++n_fans, n_fan_terms += (int)g.fan.size();
     }
 
     /* fill the tile with the highest unused lanes when fewer than T were needed (keeps the
@@ -432,7 +506,44 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         const bool is_x = g.mux < 0 && g.m[0] == 0. && g.m[1] == 0. && g.m[6] == 0. && g.m[7] == 0. && g.m[2] == 1. &&
                           g.m[3] == 0. && g.m[4] == 1. && g.m[5] == 0.;
         uint64_t sel_out = 0; /* lanes outside the tile whose parity picks the second matrix / factor */
-        if (gate_is_diag(g)) {
+        int fan_idx = -1;
+        if (!g.fan.empty()) {
+            /* phase fan: the hub is one more control; the terms are sorted by where their lane lives in
+             * this stage (thread bit / outside the tile / register bit) */
+            op.kind = OP_FAN;
+            if (in_tile)
+                ct |= 1u << lane_to_tile[g.target];
+            else
+                op.ctrl_out |= 1ull << g.target;
+            op.m[0] = op.m[2] = (real)1;
+            fan_idx = prog.n_fans++;
+            op.bit = fan_idx;
+            auto &fn = prog.fan[fan_idx];
+            fn.first = (int16_t)prog.n_fan_terms;
+            fn.n_thr = fn.n_out = fn.n_reg = 0;
+            for (int cls = 0; cls < 3; ++cls) /* 0: thread bits, 1: outside, 2: register bits */
+                for (const Gate::FanTerm &t : g.fan) {
+                    const bool inside = (S >> t.lane) & 1ull;
+                    const int j = inside ? regbit(t.lane) : -1;
+                    const int c = !inside ? 1 : (j >= 0 ? 2 : 0);
+                    if (c != cls) continue;
+                    auto &ft = prog.fan_term[prog.n_fan_terms++];
+                    ft.re = t.re, ft.im = t.im, ft.pad_ = 0;
+                    if (cls == 0) {
+                        int pos = -1;
+                        for (int i = 0; i < T - K; ++i)
+                            if (st.W[i] == lane_to_tile[t.lane]) pos = i;
+                        ft.bit = pos;
+                        ++fn.n_thr;
+                    } else if (cls == 1) {
+                        ft.bit = t.lane;
+                        ++fn.n_out;
+                    } else {
+                        ft.bit = j;
+                        ++fn.n_reg;
+                    }
+                }
+        } else if (gate_is_diag(g)) {
             const uint64_t lanes = gate_diag_lanes(g);
             const bool d0_is_one = g.parity == 0 && (g.m[0] == 1. && g.m[1] == 0.);
             if (d0_is_one) {
@@ -577,6 +688,8 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         }
         if (op.kind == OP_GEN || op.kind == OP_SHEAR)
             op.arm = ARM_GEN(op.bit) | mux_arm;
+        else if (op.kind == OP_FAN)
+            op.arm = ARM_DIAG_THR;
         else if (op.kind == OP_SWAP)
             op.arm = ARM_SWAP(op.bit);
         else
@@ -602,6 +715,18 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                 ++stats.direct_ops, ++prog.n_direct;
         } else if (op.kind == OP_SWAP) {
             op.code = OPC_SWAP(op.bit);
+        } else if (op.kind == OP_FAN) {
+            op.code = OPC_FAN;
+            /* register-bit terms: the registers (as relabelled by the stage's shears) whose bit j is
+             * set, among those the hub predicate admits */
+            auto &fn = prog.fan[fan_idx];
+            for (int k = 0; k < fn.n_reg; ++k) {
+                const int j = prog.fan_term[fn.first + fn.n_thr + fn.n_out + k].bit;
+                uint16_t mask = 0;
+                for (int r = 0; r < (1 << K); ++r)
+                    if (((roff_of(r) >> st.R[j]) & 1u) && ((op.regmask >> r) & 1u)) mask |= (uint16_t)(1u << r);
+                fn.reg_mask[k] = mask;
+            }
         } else {
             /* regsel != 0 or a relabelled register part: the register-diagonal body (it also serves
              * regsel == 0 after a relabelling turned every register to the same side) */
@@ -724,6 +849,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         /* phases nothing could absorb: their place is right after this pass */
         if (!deferred.empty()) queue.insert(queue.begin(), deferred.begin(), deferred.end());
     }
+    stats.fan_ops = prog.n_fans;
     stats.gates_in_pass = (int)picked.size();
     stats.ops_in_pass = n_ops;
     stats.stages_in_pass = n_stages;

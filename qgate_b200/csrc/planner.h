@@ -39,13 +39,14 @@ struct PlanStats {
     int shear_ops = 0;    /* dense gates lowered as OP_SHEAR                                  */
     int direct_ops = 0;   /* dense gates lowered as OP_GEN (direct 2x2)                       */
     int residual_ops = 0; /* diagonal ops added for phases no later gate could absorb          */
+    int fan_ops = 0;      /* phase fans (OP_FAN)                                               */
 };
 
 /* merge `g` into the queue: an uncontrolled gate folds into the previous gate on the same
  * lane when nothing in between touches that lane; a controlled gate folds into an
- * identical-signature gate directly before it.  Returns true when merged (queue size
- * unchanged). */
-bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge);
+ * identical-signature gate directly before it; with `fans`, controlled phases that share a lane
+ * collect into one phase fan (Gate::fan).  Returns true when merged (queue size unchanged). */
+bool enqueue_gate(std::vector<Gate> &queue, const Gate &g, bool merge, bool fans = true);
 
 /* Plan ONE pass from the front of `queue` for a state vector of n_lanes lanes.  Executed
  * gates are removed from `queue` (order of the remaining gates is preserved).  Always

@@ -17,6 +17,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 namespace qgb {
 
 enum OpKind : int {
@@ -27,6 +29,15 @@ enum OpKind : int {
     OP_DIAG_OUT = 3, /* diag on a lane OUTSIDE the tile (`bit` = state-vector lane): the CTA  */
                      /* picks d0 or d1 from its base index                                    */
     OP_SWAP = 5,     /* exchange the two amplitudes of register bit `bit` (X, CX, CCX ...)    */
+    OP_FAN = 7,      /* phase fan: a product of controlled-phase gates that share one lane (the */
+                     /* hub): amplitudes whose hub bit is 1 are multiplied by the product of    */
+                     /* e^{i phi_j} over the fan's lanes j that are 1.  The hub is lowered as a  */
+                     /* control (cmt / regmask / ctrl_out); the lanes j are PassProgram::fan_term */
+                     /* entries, sorted by where lane j lives in the op's stage: thread bits (one */
+                     /* factor per thread, from two small tables the kernel builds once per CTA), */
+                     /* lanes outside the tile (one factor per tile), register bits (one more     */
+                     /* phase on the registers of Fan::reg_mask).  A QFT's n - 1 - i controlled    */
+                     /* phases onto lane i are ONE op (Gate::fan).                                */
     OP_SHEAR = 6,    /* 2x2 on register bit `bit` as THREE complex shears, in place:           */
                      /*   q0 += y q1;  q1 += g q0;  q0 += x q1        (m = y, g, x, 0)          */
                      /* = N q for the unit-determinant matrix N = [[1,x],[0,1]] [[1,0],[g,1]]   */
@@ -49,7 +60,9 @@ enum OpKind : int {
 #define QGB_MAX_REG_BITS 4
 #define QGB_MAX_LANES 40
 #define QGB_MAX_STAGES 40
-#define QGB_MAX_OPS 112
+#define QGB_MAX_OPS 48      /* (the fused pass kernel keeps one predicate bit per op: it runs at most 32) */
+#define QGB_MAX_FANS 12     /* phase fans per pass                                                     */
+#define QGB_MAX_FAN_TERMS 384
 #define QGB_MAX_GROUPS 4    /* tensor-map dimensions above the 128-byte row (TMA staging)    */
 
 /* One op of a stage.  The control predicate of an amplitude with tile index e = ebase | roff(r)
@@ -90,6 +103,7 @@ struct Op {
                                                     /* where a thread-bit / outside multiplexer is 1) */
 #define OPC_SHEAR_MASKED(j) (36 + (j))              /* the same under register-bit controls (regmask) */
 #define OPC_SHEAR_REGMUX(j, j2) (40 + 4 * (j) + (j2)) /* multiplexed by register bit j2               */
+#define OPC_FAN 30                                  /* phase fan; Op::bit = index into PassProgram::fan */
 #define OPC_COUNT 56
 
 /* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
@@ -153,6 +167,24 @@ struct PassProgram {
     } out[QGB_MAX_OPS];
     Stage stage[QGB_MAX_STAGES];
     Op<real> op[QGB_MAX_OPS];
+    /* phase fans (OP_FAN, Op::bit = fan number): fan f multiplies the amplitudes the op's control
+     * predicate admits (hub bit 1) by the product of its terms whose bit is 1.  Terms
+     * [first, first + n_thr) test bit `bit` of the THREAD number (thread bit i <-> tile bit W[i] of
+     * the op's stage), the next n_out terms test state-vector lane `bit` of the tile's origin, the
+     * last n_reg terms apply to the registers of reg_mask[k] (register bit `bit`, already restricted
+     * to the op's regmask and expressed in relabelled registers).  Factors are kept in double in
+     * both precisions: the kernel multiplies them in double and rounds the product once. */
+    int32_t n_fans;
+    int32_t n_fan_terms;
+    struct Fan {
+        int16_t first, n_thr, n_out, n_reg;
+        uint16_t reg_mask[QGB_MAX_REG_BITS];
+    } fan[QGB_MAX_FANS];
+    struct FanTerm {
+        double re, im;
+        int32_t bit;
+        int32_t pad_;
+    } fan_term[QGB_MAX_FAN_TERMS];
 };
 
 /* Cut the lanes [row_lanes, n) of tile-lane set S into tensor-map groups (see PassProgram).
@@ -205,11 +237,28 @@ struct Gate {
      * has an even number of those bits set are multiplied by (m[0], m[1]), the others by
      * (m[6], m[7]).  An ordinary diagonal gate is the case parity == 1 << target. */
     uint64_t parity = 0;
+    /* phase fan (made by the host-side merging only, planner.cpp enqueue_gate): with a non-empty
+     * `fan` the gate is the product over the terms of the controlled phase CP(target, lane; e^{i phi})
+     * — amplitudes with bit `target` (the hub) AND bit `lane` set are multiplied by (re, im).
+     * m is the identity, ctrl_mask 0. */
+    struct FanTerm {
+        int32_t lane;
+        double re, im;
+    };
+    std::vector<FanTerm> fan;
 };
 
-inline uint64_t gate_diag_lanes(const Gate &g) { return g.parity ? g.parity : (1ull << g.target); }
+inline uint64_t gate_fan_lanes(const Gate &g) {
+    uint64_t lanes = 0;
+    for (const Gate::FanTerm &t : g.fan) lanes |= 1ull << t.lane;
+    return lanes;
+}
+inline uint64_t gate_diag_lanes(const Gate &g) {
+    return (g.parity ? g.parity : (1ull << g.target)) | gate_fan_lanes(g);
+}
 
 inline bool gate_is_diag(const Gate &g) {
+    if (!g.fan.empty()) return true;
     if (g.mux >= 0) return false; /* multiplexed gates are only formed when the result is dense */
     return g.m[2] == 0. && g.m[3] == 0. && g.m[4] == 0. && g.m[5] == 0.;
 }

@@ -9,6 +9,8 @@
  *
  * Test infrastructure only: built and run by tests/test_planner.py, never shipped.
  */
+#include <algorithm>
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +26,7 @@ static int g_failures = 0;
 static bool g_expect_tma = false;
 static long g_warp_local = 0;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
+static long g_fan_ops = 0, g_fan_thr = 0, g_fan_out = 0, g_fan_reg = 0;
 static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0, g_parity_split = 0, g_parity_gates = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
@@ -35,6 +38,14 @@ static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0,
     } while (0)
 
 static void apply_direct(std::vector<cd> &amp, int n, const Gate &g) {
+    if (!g.fan.empty()) { /* product of CP(target, lane) */
+        for (uint64_t i = 0; i < (1ull << n); ++i) {
+            if (!((i >> g.target) & 1ull)) continue;
+            for (const Gate::FanTerm &t : g.fan)
+                if ((i >> t.lane) & 1ull) amp[i] *= cd(t.re, t.im);
+        }
+        return;
+    }
     const cd m00(g.m[0], g.m[1]), m01(g.m[2], g.m[3]), m10(g.m[4], g.m[5]), m11(g.m[6], g.m[7]);
     if (g.parity) { /* d0 on an even number of set lanes, d1 on an odd number */
         for (uint64_t i = 0; i < (1ull << n); ++i)
@@ -196,6 +207,7 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                         uint32_t want = 0;
                         if (op.kind == OP_GEN || op.kind == OP_SHEAR) want = ARM_GEN(op.bit) | (op.arm & (ARM_MUX_THR | ARM_MUX_REG | ARM_MUX_OUT));
                         else if (op.kind == OP_SWAP) want = ARM_SWAP(op.bit);
+                        else if (op.kind == OP_FAN) want = ARM_DIAG_THR;
                         else want = op.regsel ? ARM_DIAG_REG : ARM_DIAG_THR;
                         CHECK(op.arm == want, "arm selector %u of op kind %d bit %d", op.arm, op.kind, op.bit);
                         /* Op::code, the body selector of the TMA-staged kernel */
@@ -217,6 +229,8 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                                 code = op.regmask == all_regs ? OPC_GEN(op.bit) : OPC_GEN_MASKED(op.bit);
                         } else if (op.kind == OP_SWAP) {
                             code = OPC_SWAP(op.bit);
+                        } else if (op.kind == OP_FAN) {
+                            code = OPC_FAN;
                         } else {
                             code = op.regsel ? OPC_DIAG_REG : OPC_DIAG_THR;
                         }
@@ -292,6 +306,36 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                             const bool one = (((op.regsel >> r) & 1u) != 0) ^ ((__builtin_popcount(ebase & op.tsel) & 1) != 0) ^ out_sel;
                             a[r] *= one ? m1 : m0;
                         }
+                    } else if (op.kind == OP_FAN) {
+                        /* as kernels_tma.cu: one factor per thread (thread-bit terms) and tile (outside
+                         * terms) on the registers of regmask, then one phase per register-bit term */
+                        CHECK(op.bit >= 0 && op.bit < p.n_fans, "fan index %d out of range", op.bit);
+                        const auto &fn = p.fan[op.bit];
+                        CHECK(fn.first >= 0 && fn.first + fn.n_thr + fn.n_out + fn.n_reg <= p.n_fan_terms, "fan terms out of range");
+                        if (tid == 0 && bid == 0) ++g_fan_ops, g_fan_thr += fn.n_thr, g_fan_out += fn.n_out, g_fan_reg += fn.n_reg;
+                        cd f(1., 0.);
+                        for (int k = 0; k < fn.n_thr; ++k) {
+                            const auto &t = p.fan_term[fn.first + k];
+                            CHECK(t.bit >= 0 && t.bit < T - K, "fan thread bit %d out of range", t.bit);
+                            if ((tid >> t.bit) & 1u) f *= cd(t.re, t.im);
+                        }
+                        for (int k = 0; k < fn.n_out; ++k) {
+                            const auto &t = p.fan_term[fn.first + fn.n_thr + k];
+                            bool in_tile = false;
+                            for (int tt = 0; tt < T; ++tt) in_tile = in_tile || p.tile_lane[tt] == t.bit;
+                            CHECK(!in_tile && t.bit >= 0 && t.bit < n, "fan outside lane %d is a tile lane", t.bit);
+                            if ((base >> t.bit) & 1ull) f *= cd(t.re, t.im);
+                        }
+                        f = cd((real)f.real(), (real)f.imag());
+                        for (int r = 0; r < (1 << K); ++r)
+                            if (((op.regmask >> r) & 1u) && active) a[r] *= f;
+                        for (int k = 0; k < fn.n_reg; ++k) {
+                            const auto &t = p.fan_term[fn.first + fn.n_thr + fn.n_out + k];
+                            CHECK(t.bit >= 0 && t.bit < K && (fn.reg_mask[k] & ~op.regmask) == 0, "fan register term %d", t.bit);
+                            const cd ft((real)t.re, (real)t.im);
+                            for (int r = 0; r < (1 << K); ++r)
+                                if (((fn.reg_mask[k] >> r) & 1u) && active) a[r] *= ft;
+                        }
                     } else {
                         CHECK(false, "unknown op kind %d", op.kind);
                     }
@@ -363,6 +407,89 @@ static Gate random_gate(std::mt19937_64 &rng, int n, int max_ctrl) {
         break;
     }
     return g;
+}
+
+/* QFT-like circuits: H on lane i, then controlled phases between lane i and every other lane (in
+ * either direction, in a shuffled order, some twice), sprinkled with random gates */
+template <typename real>
+static void run_qft_case(int n, int T, int L, int K, int max_cost, bool textbook, int noise, uint64_t seed) {
+    std::mt19937_64 rng(seed);
+    std::vector<cd> ref(1ull << n), amp;
+    std::normal_distribution<double> nd;
+    for (auto &v : ref) v = cd(nd(rng), nd(rng));
+    amp = ref;
+    std::vector<Gate> queue;
+    int n_gates = 0, n_merged = 0;
+    auto submit = [&](const Gate &g) {
+        apply_direct(ref, n, g);
+        n_merged += enqueue_gate(queue, g, true) ? 1 : 0;
+        ++n_gates;
+    };
+    const double r = std::sqrt(0.5);
+    auto had = [&](int lane) {
+        Gate g;
+        for (int e = 0; e < 8; ++e) g.m[e] = 0.;
+        g.m[0] = g.m[2] = g.m[4] = r, g.m[6] = -r;
+        g.target = lane, g.ctrl_mask = 0;
+        return g;
+    };
+    auto cp = [&](int ctrl, int target, double phi) {
+        Gate g;
+        for (int e = 0; e < 8; ++e) g.m[e] = 0.;
+        g.m[0] = 1., g.m[6] = std::cos(phi), g.m[7] = std::sin(phi);
+        g.target = target, g.ctrl_mask = 1ull << ctrl;
+        return g;
+    };
+    for (int i = 0; i < n; ++i) {
+        if (!textbook) submit(had(i));
+        std::vector<int> others;
+        if (textbook)
+            for (int j = 0; j < i; ++j) others.push_back(j);
+        else
+            for (int j = i + 1; j < n; ++j) others.push_back(j);
+        std::shuffle(others.begin(), others.end(), rng);
+        for (int j : others) {
+            const double phi = 3.141592653589793 / (double)(1 << std::abs(j - i));
+            submit((rng() & 1) ? cp(j, i, phi) : cp(i, j, phi));
+            if (rng() % 7 == 0) submit(cp(j, i, 0.3));
+            if (noise && (int)(rng() % 10) < noise) submit(random_gate(rng, n, 2));
+        }
+        if (textbook) submit(had(i));
+    }
+    PlanConfig cfg;
+    cfg.fp32 = sizeof(real) == 4;
+    cfg.K = K;
+    cfg.max_cost = max_cost;
+    cfg.T = T;
+    cfg.L = L;
+    cfg.max_ops = 32;
+    cfg.shear = true;
+    cfg.row_lanes = cfg.fp32 ? 4 : 3;
+    cfg.max_groups = QGB_MAX_GROUPS;
+    cfg.L = std::max(cfg.L, cfg.row_lanes);
+    g_expect_tma = n > cfg.row_lanes && std::min(T, n) >= cfg.row_lanes;
+    static PassProgram<real> prog;
+    int n_pass = 0;
+    const long fans_before = g_fan_ops;
+    while (!queue.empty()) {
+        PlanStats st;
+        plan_pass<real>(queue, n, cfg, prog, st);
+        CHECK(st.gates_in_pass > 0 && n_pass < 100000, "planner made no progress");
+        if (st.gates_in_pass <= 0 || n_pass >= 100000) return;
+        CHECK(prog.n_fans <= QGB_MAX_FANS && prog.n_fan_terms <= QGB_MAX_FAN_TERMS, "fan limits exceeded");
+        emulate_pass<real>(prog, amp);
+        ++n_pass;
+    }
+    double err = 0., scale = 0.;
+    for (size_t i = 0; i < ref.size(); ++i) {
+        err = std::max(err, std::abs(ref[i] - amp[i]));
+        scale = std::max(scale, std::abs(ref[i]));
+    }
+    const double tol = sizeof(real) == 4 ? 2e-4 : 1e-11;
+    CHECK(err <= tol * scale, "qft-like n=%d T=%d L=%d: rel err %.3g", n, T, L, err / scale);
+    std::printf("ok %s qft-like%s n=%2d T=%2d L=%d gates=%4d merged=%4d passes=%3d fan ops=%3ld relerr=%.2e\n",
+                sizeof(real) == 4 ? "f32" : "f64", textbook ? " (textbook order)" : "", n, T, L, n_gates, n_merged, n_pass,
+                g_fan_ops - fans_before, err / scale);
 }
 
 template <typename real>
@@ -464,6 +591,15 @@ int main() {
         }
         run_case<double>(n, 10, 5, 300, 2, 6, 3, true, seed++, true, 4, 0, true);
     }
+    /* phase fans (OP_FAN): QFT-like circuits in both gate orders, clean and with random gates mixed in */
+    for (int n : {9, 12, 14, 16}) {
+        for (int noise : {0, 2}) {
+            run_qft_case<double>(n, 10, 4, 4, 24, false, noise, seed++);
+            run_qft_case<double>(n, 10, 4, 4, 24, true, noise, seed++);
+            run_qft_case<float>(n, 11, 5, 4, 21, false, noise, seed++);
+            run_qft_case<double>(n, 9, 3, 3, 1 << 20, true, noise, seed++);
+        }
+    }
     g_expect_tma = false;
     run_case<double>(11, 8, 3, 400, 2, 16, 3, true, seed++, false, 0, 0, true);
     /* limits and no-merge paths */
@@ -490,6 +626,12 @@ int main() {
     }
     if (g_shear == 0 || g_direct == 0 || g_flipped_stages == 0 || g_residual_ops == 0) {
         std::printf("FAIL: a shear path was never exercised\n");
+        return 1;
+    }
+    std::printf("phase fans %ld: terms on thread bits %ld, outside the tile %ld, on register bits %ld\n", g_fan_ops, g_fan_thr,
+                g_fan_out, g_fan_reg);
+    if (g_fan_ops == 0 || g_fan_thr == 0 || g_fan_out == 0 || g_fan_reg == 0) {
+        std::printf("FAIL: a phase-fan term placement was never exercised\n");
         return 1;
     }
     std::printf("warp-local stage transitions checked: %ld\n", g_warp_local);

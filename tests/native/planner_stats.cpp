@@ -23,7 +23,26 @@ int main(int argc, char **argv) {
     std::uniform_real_distribution<double> u(0., 6.283185307179586);
     std::vector<Gate> queue;
     long submitted = 0, merged = 0;
-    for (int d = 0; d < depth; ++d) {
+    const bool qft = getenv("QGB_STATS_QFT") != nullptr; /* QFT instead of the bench circuit (depth ignored) */
+    for (int i = 0; qft && i < n; ++i) {
+        Gate h;
+        for (int e = 0; e < 8; ++e) h.m[e] = 0;
+        const double r = std::sqrt(0.5);
+        h.m[0] = h.m[2] = h.m[4] = r, h.m[6] = -r;
+        h.target = i, h.ctrl_mask = 0;
+        merged += enqueue_gate(queue, h, true);
+        ++submitted;
+        for (int j = i + 1; j < n; ++j) {
+            Gate g;
+            for (int e = 0; e < 8; ++e) g.m[e] = 0;
+            const double phi = 3.141592653589793 / std::ldexp(1., j - i);
+            g.m[0] = 1, g.m[6] = std::cos(phi), g.m[7] = std::sin(phi);
+            g.target = i, g.ctrl_mask = 1ull << j;
+            merged += enqueue_gate(queue, g, true);
+            ++submitted;
+        }
+    }
+    for (int d = 0; !qft && d < depth; ++d) {
         for (int i = 0; i < n; ++i) {
             const double th = u(rng), ph = u(rng), la = u(rng);
             Gate g;
@@ -53,6 +72,7 @@ int main(int argc, char **argv) {
     cfg.max_cost = max_cost; cfg.shear = shear != 0;
     if (tma) { cfg.row_lanes = 3; cfg.max_groups = QGB_MAX_GROUPS; cfg.L = std::max(cfg.L, 3); }
     static PassProgram<double> prog;
+    long fans = 0, fan_terms = 0;
     long passes = 0, ops = 0, stages = 0, gen = 0, swp = 0, diag = 0, mthr = 0, mreg = 0, mout = 0, cthr = 0, shr = 0, resid = 0, conflict = 0;
     double worst = 0.;
     while (!queue.empty()) {
@@ -60,6 +80,7 @@ int main(int argc, char **argv) {
         plan_pass<double>(queue, n, cfg, prog, st);
         ++passes;
         ops += prog.n_ops;
+        fans += prog.n_fans, fan_terms += prog.n_fan_terms;
         resid += st.residual_ops;
         for (int s = 0; s < prog.n_stages; ++s) {
             const Stage &sg = prog.stage[s];
@@ -94,5 +115,6 @@ int main(int argc, char **argv) {
                 (double)stages / passes, (double)submitted / passes);
     std::printf("ops: gen %ld (mux thread %ld, register %ld, outside %ld)  swap %ld  diag %ld  thread-controlled %ld\n", gen,
                 mthr, mreg, mout, swp, diag, cthr);
+    std::printf("phase fans %ld with %ld terms\n", fans, fan_terms);
     return 0;
 }

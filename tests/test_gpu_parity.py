@@ -27,7 +27,7 @@ PROB_TOL = {np.float64: 1e-12, np.float32: 2e-6}
 @pytest.fixture(autouse=True)
 def default_options(cuda_runtime):
     api = cuda_runtime.get_api()
-    for name, value in (('fuse', 1), ('merge', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 11),
+    for name, value in (('fuse', 1), ('merge', 1), ('fans', 1), ('tile_lanes_fp64', 10), ('tile_lanes_fp32', 11),
                         ('low_lanes_fp64', 0), ('low_lanes_fp32', 0), ('max_gates_per_pass', 112), ('max_cost', 0),
                         ('tma_buffers', 0), ('reg_bits_fp64', 4), ('ctas_per_sm', 0), ('tma_ws', 0),
                         ('warp_local', 0), ('shear_fp64', 1), ('shear_fp32', 1), ('exact', 0), ('l2_hint', 0),
@@ -667,3 +667,133 @@ def test_phase_estimation_20_bits_against_reference(cuda_runtime, ref_runtime, d
         assert np.array_equal(s_a, s_b)
     else:
         assert np.mean(s_a == s_b) > 0.995
+
+
+def fan_rich_circuit(n, seed, textbook):
+    """A QFT in either gate order with extra controlled phases (random angles, both control / target
+    orientations, repeated pairs) and a few dense gates mixed in: everything the phase-fan merging
+    (planner.cpp merge_into_fan) has to get right."""
+    rng = np.random.RandomState(seed)
+    q = S.new_qregs(n)
+    ops = [S.X(q[0]), S.X(q[2]), S.H(q[n - 1]), S.H(q[n // 2])]
+    for i in range(n):
+        others = list(range(i)) if textbook else list(range(i + 1, n))
+        rng.shuffle(others)
+        if not textbook:
+            ops.append(S.H(q[i]))
+        for j in others:
+            phi = math.pi / float(1 << abs(j - i))
+            a, b = (q[j], q[i]) if rng.randint(2) else (q[i], q[j])
+            ops.append(S.ctrl(a).U1(phi)(b))
+            if rng.randint(6) == 0:
+                ops.append(S.ctrl(q[j]).U1(float(rng.uniform(-3., 3.)))(q[i]))
+            if rng.randint(9) == 0:
+                k = int(rng.randint(n))
+                ops.append(S.U3(*[float(v) for v in rng.uniform(0., 6., 3)])(q[k]))
+            if rng.randint(11) == 0:
+                k = int(rng.randint(n - 1))
+                ops.append(S.ctrl(q[k]).X(q[k + 1]))
+        if textbook:
+            ops.append(S.H(q[i]))
+    return q, ops
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+@pytest.mark.parametrize('textbook', (False, True))
+def test_phase_fans_against_reference(cuda_runtime, ref_runtime, dtype, textbook):
+    """Controlled phases that share a lane run as ONE op (OP_FAN): same amplitudes as the reference CPU
+    runtime, which applies them one by one; the fan-less planner and several tile shapes agree too."""
+    api = cuda_runtime.get_api()
+    n = 21
+    q, ops = fan_rich_circuit(n, 5 + int(textbook), textbook)
+
+    def run(rt, **options):
+        for k, v in options.items():
+            api.set_option(k, v)
+        sim = cases.make_sim(rt, dtype, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        out = sim.qubits.states[:]
+        sim.terminate()
+        return out
+
+    want = run(ref_runtime.module)
+    exact = want
+    if dtype is np.float32:
+        sim = cases.make_sim(ref_runtime.module, np.float64, 'one_static')
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        exact = sim.qubits.states[:]
+        sim.terminate()
+    lanes = 'tile_lanes_fp64' if dtype is np.float64 else 'tile_lanes_fp32'
+    low = 'low_lanes_fp64' if dtype is np.float64 else 'low_lanes_fp32'
+    k = 4
+    api.stats_reset()
+    got = run(cuda_runtime, fans=1)
+    stats = api.stats()
+    assert stats['fan_ops'] >= n - 3, stats
+    assert cases.rel_err(got, exact) < cases.TOL[dtype]
+    assert cases.rel_err(got, want) < cases.TOL[dtype] + cases.rel_err(want, exact)
+    api.stats_reset()
+    plain = run(cuda_runtime, fans=0)
+    stats_plain = api.stats()
+    assert stats_plain['fan_ops'] == 0 and stats_plain['tile_passes'] > stats['tile_passes'], (stats, stats_plain)
+    tol = 1e-13 if dtype is np.float64 else 2e-6
+    assert cases.rel_err(got, plain) < tol
+    for options in ({lanes: k + 5, low: 0}, {lanes: k + 8, low: 6}, {lanes: k + 10, low: 3},
+                    {lanes: k + 6, low: 0, 'max_cost': 1000}, {lanes: k + 7, 'tma_buffers': 2, 'max_gates_per_pass': 5},
+                    {lanes: k + 6, 'tma_buffers': 3, 'tma_ws': 1}, {lanes: k + 6, 'shear': 0}):
+        api.stats_reset()
+        assert cases.rel_err(run(cuda_runtime, fans=1, **options), got) < tol, options
+        assert api.stats()['fan_ops'] > 0
+        for name in options:
+            api.set_option(name, {'max_gates_per_pass': 112, 'shear': 1, lanes: 10 if dtype is np.float64 else 11}.get(name, 0))
+    if dtype is np.float64:
+        api.set_option('reg_bits_fp64', 3)
+        assert cases.rel_err(run(cuda_runtime, fans=1, tile_lanes_fp64=9), got) < tol
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_phase_fans_on_the_one_kernel_per_gate_path(cuda_runtime, dtype):
+    """Fans formed while the tiled path was on and flushed after it was switched off expand into their
+    controlled phases."""
+    from qgate_b200.model import gate_type
+    from qgate_b200.simulator import qubits as qb
+    api = cuda_runtime.get_api()
+    n = 14
+    pairs = [(0, 3, 0.3), (0, 5, 0.7), (0, 13, -1.1), (13, 2, 0.4), (7, 0, 2.1)]
+
+    class Lane:
+        def __init__(self, l):
+            self.local = self.external = l
+    outs = []
+    for late_unfuse in (True, False):
+        api.set_option('fuse', 1)
+        qs = cuda_runtime.create_qubit_states(dtype)
+        pr = qs.processor
+        pr.initialize_qubit_states(qs, n)
+        pr.reset_qubit_states(qs)
+        for lane in range(n):
+            pr.apply_gate(gate_type.H(), False, qs, lane)
+        pr.flush(qs)
+        api.stats_reset()
+        for i, j, phi in pairs:
+            pr.apply_controlled_gate(gate_type.U1(phi), False, qs, [j], i)
+        if late_unfuse:
+            api.set_option('fuse', 0)   # the queued fans now go down the simple path
+        pr.flush(qs)
+        amp = np.empty(1 << n, np.complex128 if dtype is np.float64 else np.complex64)
+        getter = cuda_runtime.create_qubits_states_getter(dtype)
+        getter.get_states(amp, 0, qb.null, [(qs, [Lane(l) for l in range(n)])], [], 1 << n, 0, 1)
+        outs.append(amp)
+        stats = api.stats()
+        assert (stats['fan_ops'] >= 1) == (not late_unfuse), stats
+        getter.delete()
+        qs.delete()
+    api.set_option('fuse', 1)
+    want = np.full(1 << n, 2. ** (-n / 2.), np.complex128)
+    idx = np.arange(1 << n)
+    for i, j, phi in pairs:
+        want = want * np.where(((idx >> i) & 1) & ((idx >> j) & 1), np.exp(1j * phi), 1.)
+    for amp in outs:
+        assert cases.rel_err(amp, want) < cases.TOL[dtype]
