@@ -214,6 +214,7 @@ struct Options {
     int64_t fuse = 1;
     int64_t merge = 1;
     int64_t fans = 1; /* controlled phases that share a lane merge into one phase fan (program.h OP_FAN) */
+    int64_t fan_cost = 2;
     /* 1: every gate as submitted, one kernel each, in the reference CPU runtime's arithmetic
      * operation by operation (CPUQubitProcessor.cpp:316-324): amplitudes bit-identical to
      * qgate.simulator.cpu's.  A verification mode (one state sweep per gate), off by default. */
@@ -372,6 +373,7 @@ void flush_tiled(QStates *qs) {
     }
     cfg.max_cost = g.opt.max_cost > 0 ? (int)std::min<int64_t>(g.opt.max_cost, 1 << 30) : default_max_cost(fp32, cfg.shear);
     cfg.lookahead = (int)g.opt.lookahead;
+    cfg.fan_cost = (int)std::max<int64_t>(1, g.opt.fan_cost);
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
     PlanStats st;
     while (!qs->queue.empty()) {
@@ -388,6 +390,11 @@ void flush_tiled(QStates *qs) {
         g.stats.shear_ops += st.shear_ops;
         g.stats.direct_ops += st.direct_ops;
         g.stats.fan_ops += st.fan_ops;
+        for (int f = 0; f < prog.n_fans; ++f)
+            if (prog.fan[f].n_out > 0) { /* fan_tile_table_kernel ran before the pass */
+                g.stats.kernel_launches += 1;
+                break;
+            }
     }
 }
 
@@ -663,6 +670,7 @@ int qgb_devices_clear(void) {
     for (Pool *p : g.pools) p->d_cum = p->d_sums = nullptr;
     close_all_ipc_mappings();
     g.pool.clear();
+    tma_pass_release();
     if (g.h_gather) cudaFreeHost(g.h_gather);
     g.h_gather = nullptr;
     g.gather_bytes = 0;
@@ -1684,6 +1692,7 @@ int qgb_set_option(const char *name, int64_t value) {
     if (k == "fuse") g.opt.fuse = value;
     else if (k == "merge") g.opt.merge = value;
     else if (k == "fans") g.opt.fans = value;
+    else if (k == "fan_cost") g.opt.fan_cost = value;
     else if (k == "exact") g.opt.exact = value;
     else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
     else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;

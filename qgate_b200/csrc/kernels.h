@@ -43,6 +43,7 @@ cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf,
 /* shared memory of one CTA: n_buf tiles, the matrices of n_ops ops, n_stages thread tables */
 size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops, int n_fans);
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);
+void tma_pass_release(); /* frees the scratch of the phase-fan tile tables */
 void tma_pass_set_warp_specialised(int on); /* 1: a producer warp owns the TMA traffic (default 0) */
 void tma_pass_set_l2_hint(int mode);    /* 1: loads, 2: stores, 3: both with an L2 evict_first policy */
 void tma_pass_set_debug_mode(int mode); /* measurement only: 1 = stages without ops, 2 = no stages     */

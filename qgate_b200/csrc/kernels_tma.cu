@@ -40,6 +40,11 @@ struct TmaGeometry {
     unsigned long long *phase;       /* QGB_PHASE_TIMING=1: cycles per phase, summed over warp 0 of */
                                      /* every CTA (diagnostic build only, see tma_pass_phase_report) */
     int32_t l2_hint;                 /* 1: loads, 2: stores, 3: both carry an L2 evict_first policy  */
+    const void *fan_tiles;           /* phase fans: per fan two tables of TILE factors (device memory, */
+                                     /* built by fan_tile_table_kernel before the pass), indexed by the  */
+                                     /* low fan_lo bits of the tile number and by the rest; nullptr when */
+                                     /* no fan of the pass has a term outside the tile                   */
+    int32_t fan_lo, fan_hi;
     int32_t debug_mode;              /* measurement only (option debug_pass_mode): 1 = the stages   */
                                      /* load and store their registers but skip the ops, 2 = no     */
                                      /* stages at all (the tile only travels in and out)             */
@@ -395,6 +400,74 @@ __device__ __forceinline__ void lean_apply_shear(typename Cplx<real>::type (&a)[
     }
 }
 
+/* ---- OP_FAN: register r is multiplied by f * prod of reg[b] over the set bits b of r --------------
+ * complex128: a Gray-code walk over the registers with a running factor (one complex product per
+ * step, by reg[b] when bit b turns on, by its conjugate = inverse when it turns off), straight-line
+ * code specialised on the hub predicate — no per-register branches, so no register moves at their
+ * join points (the masked phase loop spends a third of its issue slots on them), and only four live
+ * registers of factor state.  Measured against independent per-register factors from a 16-entry
+ * constant table (32 more constant loads per fan and thread, 16% of them missing the constant
+ * cache): the walk is 20% faster (profiles/r2m).  MODE 0: every register, 1: the registers of
+ * regmask (uniform tests), 2: the registers whose bit J equals POL. */
+template <int K, int MODE, int J, int POL, typename FanT>
+__device__ __forceinline__ void fan_walk(double2 (&a)[1 << K], double fr, double fi, const FanT &fn, uint32_t regmask) {
+    constexpr int NF = MODE == 2 ? K - 1 : K; /* free register bits */
+#pragma unroll
+    for (int i = 0; i < (1 << NF); ++i) {
+        const int gray = i ^ (i >> 1);
+        if (i > 0) {
+            int fb = 0;
+            while (!((i >> fb) & 1)) ++fb; /* the free bit that changes at this step */
+            const int pb = (MODE == 2 && fb >= J) ? fb + 1 : fb;
+            const double tr = fn.reg[pb][0], ti = ((gray >> fb) & 1) ? fn.reg[pb][1] : -fn.reg[pb][1];
+            const double nr = fr * tr - fi * ti;
+            fi = fr * ti + fi * tr;
+            fr = nr;
+        }
+        int r = 0;
+#pragma unroll
+        for (int fb = 0; fb < NF; ++fb) {
+            const int pb = (MODE == 2 && fb >= J) ? fb + 1 : fb;
+            r |= ((gray >> fb) & 1) << pb;
+        }
+        if (MODE == 2) r |= POL << J;
+        if (MODE != 1 || ((regmask >> r) & 1u)) {
+            const double qr = a[r].x, qi = a[r].y;
+            a[r].x = fr * qr - fi * qi;
+            a[r].y = fr * qi + fi * qr;
+        }
+    }
+}
+template <int K, typename FanT>
+__device__ __forceinline__ void lean_apply_fan(double2 (&a)[1 << K], int code, double fr, double fi, const FanT &fn,
+                                               uint32_t regmask) {
+    switch (code) {
+    case OPC_FAN_ALL: fan_walk<K, 0, 0, 0>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(0, 0): fan_walk<K, 2, 0, 0>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(0, 1): fan_walk<K, 2, 0, 1>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(1, 0): fan_walk<K, 2, QGB_J(1), 0>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(1, 1): fan_walk<K, 2, QGB_J(1), 1>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(2, 0): fan_walk<K, 2, QGB_J(2), 0>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(2, 1): fan_walk<K, 2, QGB_J(2), 1>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(3, 0): if (K > 3) fan_walk<K, 2, QGB_J(3), 0>(a, fr, fi, fn, 0u); break;
+    case OPC_FAN_REG(3, 1): if (K > 3) fan_walk<K, 2, QGB_J(3), 1>(a, fr, fi, fn, 0u); break;
+    default: fan_walk<K, 1, 0, 0>(a, fr, fi, fn, regmask); break;
+    }
+}
+/* complex64: the packed phase multiply is two instructions per amplitude, a per-register factor would
+ * cost more in packing than it saves: the thread factor on the registers of regmask, then one phase
+ * per register bit that carries a term */
+template <int K, typename FanT>
+__device__ __forceinline__ void lean_apply_fan(float2 (&a)[1 << K], int code, float fr, float fi, const FanT &fn,
+                                               uint32_t regmask) {
+    (void)code;
+    lean_phase<K>(a, fr, fi, regmask);
+    const uint32_t bit_set[4] = {0xaaaau, 0xccccu, 0xf0f0u, 0xff00u};
+#pragma unroll
+    for (int b = 0; b < K; ++b)
+        if ((fn.n_reg >> b) & 1) lean_phase<K>(a, (float)fn.reg[b][0], (float)fn.reg[b][1], regmask & bit_set[b]);
+}
+
 /* One op on the registers of a thread that takes part in it (`mm` = the op's matrix or factor
  * already selected for this thread and tile, `mo` = the op's [m | m1] block).  The matrix is
  * fetched BEFORE the dispatch so the shared-memory latency hides under the switch. */
@@ -462,7 +535,7 @@ __device__ __forceinline__ void lean_apply_op(typename Cplx<real>::type (&a)[1 <
  * timing build).  Consumers synchronise among themselves on a named barrier.  Measured 5-7%
  * SLOWER than the unspecialised kernel (the other resident CTAs already cover that wait, the
  * extra warp costs registers): kept as an option, off by default. */
-template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT>
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT, bool FANS>
 __global__ void __launch_bounds__(NT, MINB)
 tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_constant__ CUtensorMap tmap,
                 const __grid_constant__ TmaGeometry geo) {
@@ -526,28 +599,25 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             base |= (uint64_t)(((uint32_t)(t >> geo.shift[d])) & geo.mask[d]) << geo.base_shift[d];
         return base;
     };
-    /* fan f's factor for the tile at `base`: the product of its outside-the-tile terms whose lane is 1
-     * (in double, rounded once) */
-    auto fan_tile_factor = [&](int f, uint64_t base) {
-        const auto &fn = prog.fan[f];
-        double pr = 1., pi = 0.;
-        for (int k = fn.first + fn.n_thr; k < fn.first + fn.n_thr + fn.n_out; ++k) {
-            const auto &tm = prog.fan_term[k];
-            if ((base >> tm.bit) & 1ull) {
-                const double r = pr * tm.re - pi * tm.im;
-                pi = pr * tm.im + pi * tm.re;
-                pr = r;
-            }
-        }
+    /* fan f's factor for tile number t: its terms on lanes outside the tile, from the two tables
+     * fan_tile_table_kernel built for this pass (one entry per value of the low / high tile-number bits) */
+    auto fan_tile_factor = [&](int f, uint64_t t) {
         cplx out;
-        out.x = (real)pr, out.y = (real)pi;
+        out.x = (real)1, out.y = (real)0;
+        if (geo.fan_tiles) {
+            const cplx *tab = reinterpret_cast<const cplx *>(geo.fan_tiles) + (size_t)f * ((1u << geo.fan_lo) + (1u << geo.fan_hi));
+            const cplx lo = tab[t & ((1ull << geo.fan_lo) - 1ull)], hi = tab[(1ull << geo.fan_lo) + (t >> geo.fan_lo)];
+            out.x = lo.x * hi.x - lo.y * hi.y;
+            out.y = lo.x * hi.y + lo.y * hi.x;
+        }
         return out;
     };
-    for (int i = tid; !producer && i < prog.n_fans * fan_tab_size; i += nthr) {
+    for (int i = tid; FANS && !producer && i < prog.n_fans * fan_tab_size; i += nthr) {
         const int f = i / fan_tab_size, e = i - f * fan_tab_size;
         const uint32_t x = e < (1 << FLO) ? (uint32_t)e : ((uint32_t)(e - (1 << FLO)) << FLO); /* thread-number bits */
         const auto &fn = prog.fan[f];
         double pr = 1., pi = 0.;
+        if (e < (1 << FLO)) pr = fn.base[0], pi = fn.base[1]; /* (the factor common to the whole fan) */
         for (int k = fn.first; k < fn.first + fn.n_thr; ++k) {
             const auto &tm = prog.fan_term[k];
             if ((x >> tm.bit) & 1u) {
@@ -558,7 +628,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         }
         fan_tab[i].x = (real)pr, fan_tab[i].y = (real)pi;
     }
-    if (!producer && (int)tid < prog.n_fans && blockIdx.x < n_tiles) fan_out[tid] = fan_tile_factor((int)tid, tile_base(blockIdx.x));
+    if (FANS && !producer && (int)tid < prog.n_fans && blockIdx.x < n_tiles) fan_out[tid] = fan_tile_factor((int)tid, blockIdx.x);
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < NBUF; ++b) {
@@ -650,8 +720,8 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         const uint64_t base = tile_base(t);
         /* the fans' factors of the NEXT tile, one thread per fan: published by the barrier that ends
          * this tile (the buffer written here was last read in the previous tile) */
-        if ((int)tid < prog.n_fans && t + stride < n_tiles)
-            fan_out[(fan_cur ^ 1) * prog.n_fans + tid] = fan_tile_factor((int)tid, tile_base(t + stride));
+        if (FANS && (int)tid < prog.n_fans && t + stride < n_tiles)
+            fan_out[(fan_cur ^ 1) * prog.n_fans + tid] = fan_tile_factor((int)tid, t + stride);
         uint32_t eff = act, sel = sel_thr;
         for (int i = 0; i < prog.n_out; ++i) {
             const uint64_t cm = prog.out[i].ctrl_mask;
@@ -688,21 +758,16 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
                     if (!(eff & bit)) continue;
                     const Op<real> &op = prog.op[o];
                     const real *mm = mo + ((sel & bit) ? MS : 0);
-                    if (op.code >= OPC_SHEAR(0)) {
-                        lean_apply_shear<real, K>(a, op, mo, mm);
-                    } else if (op.code == OPC_FAN) {
-                        /* one factor per thread and tile on the registers the hub predicate admits, then
-                         * one phase per term whose lane is a register bit of this stage */
-                        const auto &fn = prog.fan[op.bit];
+                    if (FANS && op.kind == OP_FAN) {
+                        /* one factor per thread and tile (thread tables x tile table), then the register
+                         * bits' factors, on the registers the hub predicate admits */
                         const cplx *tab = fan_tab + op.bit * fan_tab_size;
                         const cplx f0 = tab[tid & ((1u << FLO) - 1u)], f1 = tab[(1 << FLO) + (tid >> FLO)];
                         const cplx f2 = fan_out[fan_cur * prog.n_fans + op.bit];
                         const real gr = f0.x * f1.x - f0.y * f1.y, gi = f0.x * f1.y + f0.y * f1.x;
-                        lean_phase<K>(a, gr * f2.x - gi * f2.y, gr * f2.y + gi * f2.x, op.regmask);
-                        for (int k = 0; k < fn.n_reg; ++k) {
-                            const auto &tm = prog.fan_term[fn.first + fn.n_thr + fn.n_out + k];
-                            lean_phase<K>(a, (real)tm.re, (real)tm.im, (uint32_t)fn.reg_mask[k]);
-                        }
+                        lean_apply_fan<K>(a, op.code, gr * f2.x - gi * f2.y, gr * f2.y + gi * f2.x, prog.fan[op.bit], op.regmask);
+                    } else if (op.code >= OPC_SHEAR(0)) {
+                        lean_apply_shear<real, K>(a, op, mo, mm);
                     } else {
                         lean_apply_op<real, K, DIRECT>(a, op, mo, mm);
                     }
@@ -739,7 +804,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             b = 0;
             parity ^= 1u;
         }
-        fan_cur ^= 1;
+        if (FANS) fan_cur ^= 1;
     }
     if (!WS && tid == 0) bulk_wait_read<0>();
 #ifdef QGB_PHASE_TIMING
@@ -753,6 +818,41 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
     }
 #endif
 }
+
+/* Tile factors of the pass's phase fans.  Tile number t addresses the lanes outside the tile (bit i of
+ * t <-> PassProgram::rest_lane[i]); a fan's factor for a tile is the product of its outside terms whose
+ * lane is 1 in the tile's origin, and splits into a factor of the low `lo` bits of t and one of the
+ * rest: out[f][e] for e < 2^lo, out[f][2^lo + e] for the high part.  One thread per entry; the term
+ * loop is uniform (constant-bank broadcasts), products in double, rounded once. */
+template <typename real>
+__global__ void __launch_bounds__(256)
+fan_tile_table_kernel(const __grid_constant__ PassProgram<real> prog, int lo, int hi, typename Cplx<real>::type *out) {
+    const uint32_t per_fan = (1u << lo) + (1u << hi);
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_fan * (uint32_t)prog.n_fans) return;
+    const int f = (int)(idx / per_fan);
+    const uint32_t e = idx - (uint32_t)f * per_fan;
+    const bool high = e >= (1u << lo);
+    const uint32_t bits = high ? e - (1u << lo) : e;
+    const int first = high ? lo : 0, count = high ? hi : lo;
+    uint64_t base = 0;
+    for (int i = 0; i < count; ++i) base |= (uint64_t)((bits >> i) & 1u) << prog.rest_lane[first + i];
+    const auto &fn = prog.fan[f];
+    double pr = 1., pi = 0.;
+    for (int k = fn.first + fn.n_thr; k < fn.first + fn.n_thr + fn.n_out; ++k) {
+        const auto &tm = prog.fan_term[k];
+        if ((base >> tm.bit) & 1ull) {
+            const double r = pr * tm.re - pi * tm.im;
+            pi = pr * tm.im + pi * tm.re;
+            pr = r;
+        }
+    }
+    out[idx].x = (real)pr;
+    out[idx].y = (real)pi;
+}
+
+void *g_fan_tiles = nullptr; /* scratch of the tile-factor tables (passes run in stream order) */
+size_t g_fan_tiles_bytes = 0;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -792,6 +892,8 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     geo->phase = g_phase;
     geo->l2_hint = g_tma_l2_hint;
     geo->debug_mode = g_tma_debug_mode;
+    geo->fan_tiles = nullptr;
+    geo->fan_lo = geo->fan_hi = 0;
     for (int d = 0; d < QGB_MAX_GROUPS; ++d) {
         if (d < prog.n_groups) {
             const int s = prog.grp_start[d], t = prog.grp_t[d], r = prog.grp_r[d];
@@ -822,11 +924,11 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT>
+template <typename real, int K, int NT, int MINB, int NBUF, bool WS, bool DIRECT, bool FANS>
 cudaError_t launch_tma_variant2(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
                                 size_t smem, cudaStream_t stream) {
     static int configured = 0;
-    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF, WS, DIRECT>;
+    auto kernel = tma_pass_kernel<real, K, NT, MINB, NBUF, WS, DIRECT, FANS>;
     if (!configured) {
         cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_max_smem);
         if (rc != cudaSuccess) return rc;
@@ -848,8 +950,11 @@ cudaError_t launch_tma_variant2(const PassProgram<real> &prog, const CUtensorMap
 template <typename real, int K, int NT, int MINB, int NBUF, bool WS>
 cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap &map, const TmaGeometry &geo,
                                size_t smem, cudaStream_t stream) {
-    if (prog.n_direct == 0) return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, false>(prog, map, geo, smem, stream);
-    return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, true>(prog, map, geo, smem, stream);
+    /* (and the fan bodies only into the one that serves passes with phase fans) */
+    if (prog.n_fans > 0 && prog.n_direct == 0) return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, false, true>(prog, map, geo, smem, stream);
+    if (prog.n_fans > 0) return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, true, true>(prog, map, geo, smem, stream);
+    if (prog.n_direct == 0) return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, false, false>(prog, map, geo, smem, stream);
+    return launch_tma_variant2<real, K, NT, MINB, NBUF, WS, true, false>(prog, map, geo, smem, stream);
 }
 
 template <typename real, int K>
@@ -861,6 +966,32 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
     TmaGeometry geo;
     rc = encode_map<real>(prog, amp, &map, &geo);
     if (rc != cudaSuccess) return rc;
+    {
+        int n_out_terms = 0;
+        for (int f = 0; f < prog.n_fans; ++f) n_out_terms += prog.fan[f].n_out;
+        if (n_out_terms > 0) {
+            typedef typename Cplx<real>::type cplx;
+            const int nb = prog.n_lanes - prog.T;
+            geo.fan_lo = (nb + 1) / 2;
+            geo.fan_hi = nb - geo.fan_lo;
+            const size_t entries = (size_t)prog.n_fans * (((size_t)1 << geo.fan_lo) + ((size_t)1 << geo.fan_hi));
+            if (entries * sizeof(cplx) > g_fan_tiles_bytes) {
+                /* (grows a few times per process at most; freeing synchronises with the passes in flight) */
+                if (g_fan_tiles) cudaFree(g_fan_tiles);
+                g_fan_tiles = nullptr;
+                g_fan_tiles_bytes = 0;
+                const size_t want = entries * sizeof(cplx) * 2;
+                rc = cudaMalloc(&g_fan_tiles, want);
+                if (rc != cudaSuccess) return rc;
+                g_fan_tiles_bytes = want;
+            }
+            fan_tile_table_kernel<real><<<(unsigned)((entries + 255) / 256), 256, 0, stream>>>(
+                prog, geo.fan_lo, geo.fan_hi, reinterpret_cast<cplx *>(g_fan_tiles));
+            rc = cudaGetLastError();
+            if (rc != cudaSuccess) return rc;
+            geo.fan_tiles = g_fan_tiles;
+        }
+    }
     const size_t smem = tma_pass_smem_bytes(prec, prog.T, prog.K, prog.n_stages, n_buf, prog.n_ops, prog.n_fans);
     const int nthr = 1 << (prog.T - prog.K);
     (void)min_ctas;
@@ -916,6 +1047,12 @@ void tma_pass_phase_report() {
                      100. * h[0] / tot, 100. * h[1] / tot, 100. * h[2] / tot, 100. * h[3] / tot, 100. * h[4] / tot);
     cudaMemset(g_phase, 0, sizeof(h));
 #endif
+}
+
+void tma_pass_release() {
+    if (g_fan_tiles) cudaFree(g_fan_tiles);
+    g_fan_tiles = nullptr;
+    g_fan_tiles_bytes = 0;
 }
 
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {

@@ -295,7 +295,7 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         bool blocked = (xq & (blockedX | blockedZ)) || (zq & blockedX);
         const bool is_fan = !g.fan.empty();
         /* (a fan multiplies half of the amplitudes once and builds one factor per thread and tile) */
-        const int gcost = is_fan ? 2 : (diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4)));
+        const int gcost = is_fan ? cfg.fan_cost : (diag ? 1 : (gate_is_antidiag(g) ? 1 : (cfg.shear ? 3 : 4)));
         /* op slots: a sheared gate with controls or a multiplexer may need its phase applied as one
          * more (diagonal) op of this pass */
         const int gslots = (cfg.shear && !diag && (g.mux >= 0 || g.ctrl_mask != 0)) ? 2 : 1;
@@ -521,12 +521,28 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
             auto &fn = prog.fan[fan_idx];
             fn.first = (int16_t)prog.n_fan_terms;
             fn.n_thr = fn.n_out = fn.n_reg = 0;
+            fn.base[0] = 1., fn.base[1] = 0.;
+            for (int j = 0; j < QGB_MAX_REG_BITS; ++j) fn.reg[j][0] = 1., fn.reg[j][1] = 0.;
             for (int cls = 0; cls < 3; ++cls) /* 0: thread bits, 1: outside, 2: register bits */
                 for (const Gate::FanTerm &t : g.fan) {
                     const bool inside = (S >> t.lane) & 1ull;
                     const int j = inside ? regbit(t.lane) : -1;
                     const int c = !inside ? 1 : (j >= 0 ? 2 : 0);
                     if (c != cls) continue;
+                    if (cls == 2) {
+                        /* register r holds the element of register index r ^ flip: on a relabelled bit
+                         * the term belongs to the registers whose bit j is CLEAR: t everywhere, 1 / t
+                         * where the bit is set */
+                        fn.n_reg = (int16_t)(fn.n_reg | (1 << j));
+                        if (flip & (1u << j)) {
+                            const cd tt(t.re, t.im), b = cd(fn.base[0], fn.base[1]) * tt, inv = 1. / tt;
+                            fn.base[0] = b.real(), fn.base[1] = b.imag();
+                            fn.reg[j][0] = inv.real(), fn.reg[j][1] = inv.imag();
+                        } else {
+                            fn.reg[j][0] = t.re, fn.reg[j][1] = t.im;
+                        }
+                        continue;
+                    }
                     auto &ft = prog.fan_term[prog.n_fan_terms++];
                     ft.re = t.re, ft.im = t.im, ft.pad_ = 0;
                     if (cls == 0) {
@@ -535,12 +551,9 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
                             if (st.W[i] == lane_to_tile[t.lane]) pos = i;
                         ft.bit = pos;
                         ++fn.n_thr;
-                    } else if (cls == 1) {
+                    } else {
                         ft.bit = t.lane;
                         ++fn.n_out;
-                    } else {
-                        ft.bit = j;
-                        ++fn.n_reg;
                     }
                 }
         } else if (gate_is_diag(g)) {
@@ -716,17 +729,16 @@ void plan_pass(std::vector<Gate> &queue, int n_lanes, const PlanConfig &cfg,
         } else if (op.kind == OP_SWAP) {
             op.code = OPC_SWAP(op.bit);
         } else if (op.kind == OP_FAN) {
-            op.code = OPC_FAN;
-            /* register-bit terms: the registers (as relabelled by the stage's shears) whose bit j is
-             * set, among those the hub predicate admits */
-            auto &fn = prog.fan[fan_idx];
-            for (int k = 0; k < fn.n_reg; ++k) {
-                const int j = prog.fan_term[fn.first + fn.n_thr + fn.n_out + k].bit;
-                uint16_t mask = 0;
-                for (int r = 0; r < (1 << K); ++r)
-                    if (((roff_of(r) >> st.R[j]) & 1u) && ((op.regmask >> r) & 1u)) mask |= (uint16_t)(1u << r);
-                fn.reg_mask[k] = mask;
-            }
+            /* the hub predicate over the registers: all of them (hub on a thread bit or outside the
+             * tile), or the half whose bit j is 1 (0 after a relabelling of that bit) */
+            op.code = op.regmask == all_regs ? OPC_FAN_ALL : OPC_FAN;
+            for (int j = 0; j < K; ++j)
+                for (int pol = 0; pol < 2; ++pol) {
+                    uint32_t pattern = 0;
+                    for (int r = 0; r < (1 << K); ++r)
+                        if (((r >> j) & 1) == pol) pattern |= 1u << r;
+                    if (op.regmask == pattern) op.code = OPC_FAN_REG(j, pol);
+                }
         } else {
             /* regsel != 0 or a relabelled register part: the register-diagonal body (it also serves
              * regsel == 0 after a relabelling turned every register to the same side) */

@@ -30,6 +30,7 @@ struct PlanConfig {
      * the rest stays a direct 2x2 (OP_GEN) */
     bool shear = false;
     double shear_max_coef = 12.;
+    int fan_cost = 2;     /* cost of a phase fan against max_cost (sheared 2x2 = 3, diagonal = 1) */
 };
 
 struct PlanStats {

@@ -35,9 +35,10 @@ enum OpKind : int {
                      /* control (cmt / regmask / ctrl_out); the lanes j are PassProgram::fan_term */
                      /* entries, sorted by where lane j lives in the op's stage: thread bits (one */
                      /* factor per thread, from two small tables the kernel builds once per CTA), */
-                     /* lanes outside the tile (one factor per tile), register bits (one more     */
-                     /* phase on the registers of Fan::reg_mask).  A QFT's n - 1 - i controlled    */
-                     /* phases onto lane i are ONE op (Gate::fan).                                */
+                     /* lanes outside the tile (one factor per tile, from two tables in device    */
+                     /* memory built before the pass), register bits (Fan::reg: one factor per     */
+                     /* register bit, applied along a Gray-code walk over the registers).  A QFT's */
+                     /* n - 1 - i controlled phases onto lane i are ONE op (Gate::fan).            */
     OP_SHEAR = 6,    /* 2x2 on register bit `bit` as THREE complex shears, in place:           */
                      /*   q0 += y q1;  q1 += g q0;  q0 += x q1        (m = y, g, x, 0)          */
                      /* = N q for the unit-determinant matrix N = [[1,x],[0,1]] [[1,0],[g,1]]   */
@@ -103,8 +104,12 @@ struct Op {
                                                     /* where a thread-bit / outside multiplexer is 1) */
 #define OPC_SHEAR_MASKED(j) (36 + (j))              /* the same under register-bit controls (regmask) */
 #define OPC_SHEAR_REGMUX(j, j2) (40 + 4 * (j) + (j2)) /* multiplexed by register bit j2               */
-#define OPC_FAN 30                                  /* phase fan; Op::bit = index into PassProgram::fan */
-#define OPC_COUNT 56
+#define OPC_FAN 30                                  /* phase fan (Op::bit = index into PassProgram::fan) on the */
+                                                    /* registers of regmask                                    */
+#define OPC_FAN_ALL 31                              /* ... on every register (hub on a thread bit / outside)    */
+#define OPC_FAN_REG(j, pol) (56 + 2 * (j) + (pol))  /* ... on the registers whose bit j equals pol (hub = a     */
+                                                    /* register bit; pol = 0 after a relabelling of that bit)   */
+#define OPC_COUNT 64
 
 /* Shared-memory slot of tile element e: the 128-byte XOR swizzle TMA tensor maps produce
  * (byte address bits [6:4] ^= bits [9:7]).  Linear over GF(2), so
@@ -170,15 +175,17 @@ struct PassProgram {
     /* phase fans (OP_FAN, Op::bit = fan number): fan f multiplies the amplitudes the op's control
      * predicate admits (hub bit 1) by the product of its terms whose bit is 1.  Terms
      * [first, first + n_thr) test bit `bit` of the THREAD number (thread bit i <-> tile bit W[i] of
-     * the op's stage), the next n_out terms test state-vector lane `bit` of the tile's origin, the
-     * last n_reg terms apply to the registers of reg_mask[k] (register bit `bit`, already restricted
-     * to the op's regmask and expressed in relabelled registers).  Factors are kept in double in
-     * both precisions: the kernel multiplies them in double and rounds the product once. */
+     * the op's stage), the next n_out terms test state-vector lane `bit` of the tile's origin.  Terms
+     * on register bits are folded into reg[b] = the factor of the registers whose PHYSICAL bit b is
+     * set (the identity where the fan has no such term; a term on a bit the stage's shears relabelled
+     * becomes base *= t, reg[b] = 1 / t) and `base`, a factor of every amplitude the fan touches (the
+     * kernel folds it into its thread tables).  Factors are kept in double in both precisions. */
     int32_t n_fans;
     int32_t n_fan_terms;
     struct Fan {
-        int16_t first, n_thr, n_out, n_reg;
-        uint16_t reg_mask[QGB_MAX_REG_BITS];
+        int16_t first, n_thr, n_out, n_reg; /* n_reg: register bits that carry a term (bit mask) */
+        double reg[QGB_MAX_REG_BITS][2];
+        double base[2];
     } fan[QGB_MAX_FANS];
     struct FanTerm {
         double re, im;

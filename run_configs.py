@@ -199,6 +199,8 @@ def main():
     ap.add_argument('--shots', type=int, default=1000000)
     ap.add_argument('--dtype', default='f64', choices=('f64', 'f32'))
     ap.add_argument('--option', action='append', default=[], help='engine option name=value')
+    ap.add_argument('--repeat', type=int, default=1, help='run the config this many times, report the last '
+                    '(the first run pays the device allocation of the state vector)')
     args = ap.parse_args()
     if args.qubits is None:
         args.qubits = {'grover': 30, 'pe': 32, 'qft': 35}[args.config]
@@ -208,8 +210,9 @@ def main():
     for opt in args.option:
         name, value = opt.split('=')
         api.set_option(name, int(value))
-    api.stats_reset()
-    out = {'grover': run_grover, 'pe': run_pe, 'qft': run_qft}[args.config](args, torch, world, rank)
+    for _ in range(max(1, args.repeat)):
+        api.stats_reset()
+        out = {'grover': run_grover, 'pe': run_pe, 'qft': run_qft}[args.config](args, torch, world, rank)
     out['n_gpus'] = world
     out['engine_stats'] = api.stats()
     if rank == 0:

@@ -26,7 +26,7 @@ static int g_failures = 0;
 static bool g_expect_tma = false;
 static long g_warp_local = 0;
 static long g_mux_thr = 0, g_mux_reg = 0, g_mux_out = 0;
-static long g_fan_ops = 0, g_fan_thr = 0, g_fan_out = 0, g_fan_reg = 0;
+static long g_fan_ops = 0, g_fan_thr = 0, g_fan_out = 0, g_fan_reg = 0, g_fan_codes[4] = {0, 0, 0, 0};
 static long g_shear = 0, g_direct = 0, g_flipped_stages = 0, g_residual_ops = 0, g_parity_split = 0, g_parity_gates = 0;
 #define CHECK(cond, ...)                      \
     do {                                      \
@@ -230,7 +230,15 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                         } else if (op.kind == OP_SWAP) {
                             code = OPC_SWAP(op.bit);
                         } else if (op.kind == OP_FAN) {
-                            code = OPC_FAN;
+                            code = op.regmask == all_regs ? OPC_FAN_ALL : OPC_FAN;
+                            for (int j = 0; j < K; ++j)
+                                for (int pol = 0; pol < 2; ++pol) {
+                                    uint32_t pattern = 0;
+                                    for (int r = 0; r < (1 << K); ++r)
+                                        if (((r >> j) & 1) == pol) pattern |= 1u << r;
+                                    if (op.regmask == pattern) code = OPC_FAN_REG(j, pol);
+                                }
+                            if (tid == 0 && bid == 0) g_fan_codes[code == OPC_FAN ? 0 : code == OPC_FAN_ALL ? 1 : 2 + (code & 1)]++;
                         } else {
                             code = op.regsel ? OPC_DIAG_REG : OPC_DIAG_THR;
                         }
@@ -311,9 +319,9 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                          * terms) on the registers of regmask, then one phase per register-bit term */
                         CHECK(op.bit >= 0 && op.bit < p.n_fans, "fan index %d out of range", op.bit);
                         const auto &fn = p.fan[op.bit];
-                        CHECK(fn.first >= 0 && fn.first + fn.n_thr + fn.n_out + fn.n_reg <= p.n_fan_terms, "fan terms out of range");
-                        if (tid == 0 && bid == 0) ++g_fan_ops, g_fan_thr += fn.n_thr, g_fan_out += fn.n_out, g_fan_reg += fn.n_reg;
-                        cd f(1., 0.);
+                        CHECK(fn.first >= 0 && fn.first + fn.n_thr + fn.n_out <= p.n_fan_terms, "fan terms out of range");
+                        if (tid == 0 && bid == 0) ++g_fan_ops, g_fan_thr += fn.n_thr, g_fan_out += fn.n_out, g_fan_reg += __builtin_popcount(fn.n_reg);
+                        cd f(fn.base[0], fn.base[1]);
                         for (int k = 0; k < fn.n_thr; ++k) {
                             const auto &t = p.fan_term[fn.first + k];
                             CHECK(t.bit >= 0 && t.bit < T - K, "fan thread bit %d out of range", t.bit);
@@ -326,15 +334,17 @@ static void emulate_pass(const PassProgram<real> &p, std::vector<cd> &amp) {
                             CHECK(!in_tile && t.bit >= 0 && t.bit < n, "fan outside lane %d is a tile lane", t.bit);
                             if ((base >> t.bit) & 1ull) f *= cd(t.re, t.im);
                         }
-                        f = cd((real)f.real(), (real)f.imag());
-                        for (int r = 0; r < (1 << K); ++r)
-                            if (((op.regmask >> r) & 1u) && active) a[r] *= f;
-                        for (int k = 0; k < fn.n_reg; ++k) {
-                            const auto &t = p.fan_term[fn.first + fn.n_thr + fn.n_out + k];
-                            CHECK(t.bit >= 0 && t.bit < K && (fn.reg_mask[k] & ~op.regmask) == 0, "fan register term %d", t.bit);
-                            const cd ft((real)t.re, (real)t.im);
-                            for (int r = 0; r < (1 << K); ++r)
-                                if (((fn.reg_mask[k] >> r) & 1u) && active) a[r] *= ft;
+                        /* per register: the factors of its set bits (kernels_tma.cu walks the registers in
+                         * Gray-code order with a running product) */
+                        for (int j = 0; j < QGB_MAX_REG_BITS; ++j)
+                            CHECK(((fn.n_reg >> j) & 1) || (fn.reg[j][0] == 1. && fn.reg[j][1] == 0.), "fan register bit %d: factor without a term", j);
+                        CHECK((fn.n_reg >> K) == 0, "fan register bits out of range");
+                        for (int r = 0; r < (1 << K); ++r) {
+                            if (!((op.regmask >> r) & 1u) || !active) continue;
+                            cd fr = f;
+                            for (int j = 0; j < K; ++j)
+                                if (r & (1 << j)) fr *= cd(fn.reg[j][0], fn.reg[j][1]);
+                            a[r] *= cd((real)fr.real(), (real)fr.imag());
                         }
                     } else {
                         CHECK(false, "unknown op kind %d", op.kind);
@@ -630,7 +640,10 @@ int main() {
     }
     std::printf("phase fans %ld: terms on thread bits %ld, outside the tile %ld, on register bits %ld\n", g_fan_ops, g_fan_thr,
                 g_fan_out, g_fan_reg);
-    if (g_fan_ops == 0 || g_fan_thr == 0 || g_fan_out == 0 || g_fan_reg == 0) {
+    std::printf("fan bodies: masked %ld, every register %ld, half of the registers by a clear / set bit %ld / %ld\n", g_fan_codes[0],
+                g_fan_codes[1], g_fan_codes[2], g_fan_codes[3]);
+    if (g_fan_ops == 0 || g_fan_thr == 0 || g_fan_out == 0 || g_fan_reg == 0 || g_fan_codes[1] == 0 || g_fan_codes[2] == 0 ||
+        g_fan_codes[3] == 0) {
         std::printf("FAIL: a phase-fan term placement was never exercised\n");
         return 1;
     }
