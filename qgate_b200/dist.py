@@ -352,16 +352,16 @@ class DistQubitProcessor:
 
     def _scale_all(self, qs, re, im, local_ctrls=()):
         """Multiply every local amplitude (with the local controls set) by re + i im."""
-        free = [l for l in range(qs.n_local) if l not in local_ctrls]
-        if free:
-            mat = (C.c_double * 8)(re, im, 0., 0., 0., 0., re, im)
-            self._apply_raw(qs, mat, list(local_ctrls), free[0])
-        else:
-            # every local lane is a control: one of them becomes the target of diag(1, factor)
+        if local_ctrls:
+            # one control becomes the target of diag(1, factor): a (controlled) phase gate, which the
+            # engine folds into a neighbouring gate on that lane or into a phase fan
             ctrls = list(local_ctrls)
             lane = ctrls.pop()
             mat = (C.c_double * 8)(1., 0., 0., 0., 0., 0., re, im)
             self._apply_raw(qs, mat, ctrls, lane)
+        else:
+            mat = (C.c_double * 8)(re, im, 0., 0., 0., 0., re, im)
+            self._apply_raw(qs, mat, [], 0)
 
     def _apply_raw(self, qs, mat, ctrls, target):
         lp = self._lp(qs)
