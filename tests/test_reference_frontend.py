@@ -98,6 +98,39 @@ def test_reference_suite_on_the_cuda_library(reference_on_cuda_library, module):
     assert api.backend_name == 'cuda-sm_100a'
 
 
+def test_reference_openqasm_tests_on_our_reader(reference_with_our_runtime):
+    """the reference's own tests/test_openqasm.py (statement forms and error
+    behaviour) against `qgate.openqasm` as installed by qgate_b200.install (the reference's importer
+    needs PLY, which is not in this image), plus examples/qft.qasm run on the reference's cpu runtime
+    against the same circuit written with the reference's script API."""
+    qgate = reference_with_our_runtime
+    assert getattr(qgate.openqasm, '_qgate_b200', False)
+    mod = __import__('tests.test_openqasm', fromlist=['*'])
+    suite = unittest.TestLoader().loadTestsFromTestCase(mod.TestOpenQASM)
+    result = unittest.TestResult()
+    suite.run(result)
+    problems = ['{}: {}'.format(t.id(), tb.splitlines()[-1]) for t, tb in result.errors + result.failures]
+    assert not problems, '\n'.join(problems)
+    assert result.testsRun >= 19
+    import importlib
+    import math
+    RS = importlib.import_module('qgate.script')
+    prog = qgate.openqasm.load_circuit_from_file(os.path.join(reference_frontend.root(), 'examples', 'qft.qasm'))
+    gates = [op for op in prog.circuit if not isinstance(op, qgate.model.Measure)]
+    sim = qgate.simulator.cpu(dtype=np.float64)
+    sim.run([RS.X(prog.q[1])] + gates)
+    sim.qubits.set_ordering(prog.q)
+    got = sim.qubits.states[:]
+    q = RS.new_qregs(4)
+    ops = [RS.X(q[1]), RS.H(q[3]), RS.ctrl(q[2]).U1(math.pi / 2)(q[3]), RS.ctrl(q[1]).U1(math.pi / 4)(q[3]),
+           RS.ctrl(q[0]).U1(math.pi / 8)(q[3]), RS.H(q[2]), RS.ctrl(q[1]).U1(math.pi / 2)(q[2]),
+           RS.ctrl(q[0]).U1(math.pi / 4)(q[2]), RS.H(q[1]), RS.ctrl(q[0]).U1(math.pi / 2)(q[1]), RS.H(q[0])]
+    sim2 = qgate.simulator.cpu(dtype=np.float64)
+    sim2.run(ops)
+    sim2.qubits.set_ordering(q)
+    assert np.abs(got - sim2.qubits.states[:]).max() < 1e-15
+
+
 def test_simulator_sample_matches_reference_shot_for_shot(reference_with_our_runtime):
     """`Simulator.sample` (simulator.py:85-119: the whole circuit re-run per shot, one global-RNG
     draw per Measure): our front end on the oracle runtime and the real reference on its cpu
