@@ -148,10 +148,11 @@ struct MemPool {
         live_bytes -= c;
         /* Keep the block for the next qstates of this size class: cudaMalloc + cudaFree of a 16 GiB
          * state vector cost ~0.3 s each (bench.py e2e split), re-use is free and stream-ordered.
-         * Big blocks are capped: at most one per size class and 72 GiB in total; an allocation
-         * that fails trims the whole cache and retries (alloc). */
+         * Big blocks are capped: at most two per size class (a sharded state vector and the spare
+         * buffer of its push exchange) and 136 GiB in total (one 128 GiB shard); an allocation that
+         * fails trims the whole cache and retries (alloc). */
         const bool big = c > (size_t(1) << 28);
-        if (big && (!cached[c].empty() || cached_bytes + c > (size_t(72) << 30))) {
+        if (big && (cached[c].size() >= 2 || cached_bytes + c > (size_t(136) << 30))) {
             cudaFree(p);
             return;
         }

@@ -27,6 +27,19 @@
 #include "kernels.h"
 #include "tile_ops.cuh"
 
+/* build.py compiles this file twice (the complex128 and the complex64 instantiations in parallel):
+ * QGB_TMA_PART = 0 -> complex128 + the shared state and setters, 1 -> complex64.  Undefined: everything. */
+#if !defined(QGB_TMA_PART)
+#define QGB_TMA_F64 1
+#define QGB_TMA_F32 1
+#define QGB_TMA_SHARED 1
+#elif QGB_TMA_PART == 0
+#define QGB_TMA_F64 1
+#define QGB_TMA_SHARED 1
+#else
+#define QGB_TMA_F32 1
+#endif
+
 namespace qgb {
 
 namespace {
@@ -851,29 +864,47 @@ fan_tile_table_kernel(const __grid_constant__ PassProgram<real> prog, int lo, in
     out[idx].y = (real)pi;
 }
 
-void *g_fan_tiles = nullptr; /* scratch of the tile-factor tables (passes run in stream order) */
-size_t g_fan_tiles_bytes = 0;
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-EncodeTiledFn g_encode = nullptr;
+} // namespace
+
+/* state shared by the two halves of this file (one definition, in the QGB_TMA_SHARED half) */
+namespace tma_state {
+extern void *g_fan_tiles; /* scratch of the tile-factor tables (passes run in stream order) */
+extern size_t g_fan_tiles_bytes;
+extern void *g_encode_fn;
+extern unsigned long long *g_phase;
+extern int g_tma_ws; /* measured 5-7% slower than the unspecialised kernel on B200 (profiles/r1z): off */
+extern int g_tma_l2_hint;
+extern int g_tma_debug_mode;
+extern int g_tma_sm_count;
+extern int g_tma_max_smem;
+#ifdef QGB_TMA_SHARED
+void *g_fan_tiles = nullptr;
+size_t g_fan_tiles_bytes = 0;
+void *g_encode_fn = nullptr;
 unsigned long long *g_phase = nullptr;
-int g_tma_ws = 0; /* measured 5-7% slower than the unspecialised kernel on B200 (profiles/r1z): off */
+int g_tma_ws = 0;
 int g_tma_l2_hint = 0;
 int g_tma_debug_mode = 0;
 int g_tma_sm_count = 148;
 int g_tma_max_smem = 48 * 1024;
+#endif
+} // namespace tma_state
+using namespace tma_state;
+
+namespace {
 
 cudaError_t resolve_encode() {
-    if (g_encode) return cudaSuccess;
+    if (g_encode_fn) return cudaSuccess;
     void *fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t rc = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (rc != cudaSuccess) return rc;
     if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
-    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    g_encode_fn = fn;
     return cudaSuccess;
 }
 
@@ -918,7 +949,7 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     }
     if (consumed != prog.n_lanes - prog.T) return cudaErrorInvalidValue;
     const CUtensorMapDataType dt = sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    CUresult res = g_encode(map, dt, 5, amp, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult res = reinterpret_cast<EncodeTiledFn>(g_encode_fn)(map, dt, 5, amp, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return res == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
@@ -1020,6 +1051,7 @@ cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int pr
 
 } // namespace
 
+#ifdef QGB_TMA_SHARED
 size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops, int n_fans) {
     const size_t elem = prec == 1 ? 16 : 8;
     size_t tiles = n_buf * (elem << T);
@@ -1066,7 +1098,9 @@ cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
     g_tma_max_smem = max_smem_optin;
     return cudaSuccess;
 }
+#endif /* QGB_TMA_SHARED */
 
+#ifdef QGB_TMA_F64
 template <>
 cudaError_t launch_tma_pass<double>(const PassProgram<double> &prog, void *amp, int n_buf, int min_ctas,
                                     cudaStream_t stream) {
@@ -1076,7 +1110,9 @@ cudaError_t launch_tma_pass<double>(const PassProgram<double> &prog, void *amp, 
     if (prog.K == 4) return launch_tma_by_shape<double, 4>(prog, amp, 1, n_buf >= 3 ? 3 : 2, 2, stream);
     return launch_tma_by_shape<double, 3>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream);
 }
+#endif
 
+#ifdef QGB_TMA_F32
 template <>
 cudaError_t launch_tma_pass<float>(const PassProgram<float> &prog, void *amp, int n_buf, int min_ctas,
                                    cudaStream_t stream) {
@@ -1084,5 +1120,6 @@ cudaError_t launch_tma_pass<float>(const PassProgram<float> &prog, void *amp, in
         return cudaErrorInvalidValue;
     return launch_tma_by_shape<float, QGB_K32>(prog, amp, 2, n_buf >= 3 ? 3 : 2, min_ctas, stream);
 }
+#endif
 
 } // namespace qgb

@@ -128,6 +128,23 @@ class DistContext:
         self.timing = False          # bench.py: CUDA events around every exchange
         self._exchange_events = []
         self._barrier_buf = None
+        # IPC mappings of the peers' shards outlive the qstates that opened them: the engine's pool
+        # hands the next state vector of the same size the same blocks, whose handles then hit these
+        # mappings again.  Mapping a peer's 128 GiB shard costs ~0.25 s, a 16 GiB one 30 ms: without
+        # this every fresh simulator pays it per peer and buffer (profiles/r2r).  They are dropped when
+        # a sharded state of another size is created (every rank takes that decision alike) and when
+        # the runtime shuts down.
+        self.retained = {}           # mapping base -> True, each holding one reference of the engine's
+        self.retained_key = None     # (local lanes, bytes per amplitude) the retained mappings served
+
+    def drop_retained(self):
+        for base in list(self.retained):
+            try:
+                self.api.call('qgb_ipc_close', base)
+            except Exception:
+                pass
+        self.retained = {}
+        self.retained_key = None
 
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
     def bind_stream(self):
@@ -264,9 +281,14 @@ class DistQubitStates:
 
     def _close_peers(self):
         if self.peers:
+            ctx = self.ctx
+            keep = getattr(self, 'peer_key', None)
             for base in self.peer_bases:
+                if keep is not None and keep == ctx.retained_key and base not in ctx.retained:
+                    ctx.retained[base] = True          # the reference moves to the context
+                    continue
                 try:
-                    self.ctx.api.call('qgb_ipc_close', base)
+                    ctx.api.call('qgb_ipc_close', base)
                 except Exception:
                     pass
         self.peers = None
@@ -339,6 +361,17 @@ class DistQubitProcessor:
         qs.perm = list(range(n_lanes))
         qs.pending = []
         ctx.bind_stream()
+        if qs.g:
+            key = (n_lanes - qs.g, np.dtype(qs.dtype).itemsize)
+            if ctx.retained and ctx.retained_key != key:
+                # mappings kept for shards of another size pin the peers' freed blocks: close them, on
+                # every rank, before anybody allocates the new shards
+                ctx.drop_retained()
+                ctx.device_barrier()
+                if ctx.on_cuda:
+                    torch.cuda.synchronize()     # (the barrier is stream-ordered; allocation is a host call)
+            ctx.retained_key = key
+            qs.peer_key = key
         self._lp(qs).initialize_qubit_states(qs.local, n_lanes - qs.g)
         qs.reset_lane_states()
 
@@ -646,7 +679,13 @@ class DistQubitProcessor:
             # the push exchange needs a spare buffer on EVERY rank (twice the shard): ask, agree
             handle = (C.c_ubyte * 64)()
             offset = C.c_int64(0)
+            _, shard_bytes = qs.data_ptr()
+            fits = True
+            if ctx.on_cuda:                      # (a doomed 128 GiB allocation is not worth attempting)
+                fits = 2 * shard_bytes <= 0.95 * torch.cuda.mem_get_info()[1]
             try:
+                if not fits:
+                    raise RuntimeError('no room for a spare buffer')
                 self.api.call('qgb_qstates_ipc_export_alt', qs.local.ptr, handle, C.byref(offset))
                 mine = 1.
             except RuntimeError:                 # out of device memory: swap in place instead
