@@ -175,6 +175,10 @@ struct QStates {
     int n_lanes = -1;
     void *d_amp = nullptr;
     void *d_alt = nullptr; /* spare array for out-of-place exchanges (sharded states only) */
+    /* reset_qstates does not touch the array: the first fused pass starts from |0...0> without reading
+     * it (launch_tma_pass zero_input), any other consumer writes the basis state first (materialize).
+     * Saves one write + one read of the state per run: 10% of a 30-qubit QFT. */
+    bool zero_pending = false;
     /* lane map: lane l of the caller (the "local lane" of the reference's protocol) is bit perm[l]
      * of the array index.  Identity until a native Swap: exchanging two lanes is exchanging two
      * entries here, no amplitude moves (the reference expands a Swap into three
@@ -216,6 +220,7 @@ struct Options {
     int64_t merge = 1;
     int64_t fans = 1; /* controlled phases that share a lane merge into one phase fan (program.h OP_FAN) */
     int64_t fan_cost = 2;
+    int64_t lazy_reset = 1; /* |0...0> is produced by the first fused pass instead of a sweep of its own */
     /* 1: every gate as submitted, one kernel each, in the reference CPU runtime's arithmetic
      * operation by operation (CPUQubitProcessor.cpp:316-324): amplitudes bit-identical to
      * qgate.simulator.cpu's.  A verification mode (one state sweep per gate), off by default. */
@@ -381,7 +386,8 @@ void flush_tiled(QStates *qs) {
         plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
         if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
         if (prog.n_groups < 1) fail(QGB_ERR_RUNTIME, "planner produced a tile no tensor map describes.");
-        CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, 3, g.stream));
+        CUDA_CHECK(launch_tma_pass<real>(prog, qs->d_amp, n_buf, 3, g.stream, qs->zero_pending ? 1 : 0));
+        qs->zero_pending = false;
         g.stats.tma_passes += 1;
         g.stats.kernel_launches += 1;
         g.stats.tile_passes += 1;
@@ -399,8 +405,18 @@ void flush_tiled(QStates *qs) {
     }
 }
 
+void materialize(QStates *qs) {
+    if (!qs->zero_pending) return;
+    qs->zero_pending = false;
+    CUDA_CHECK(launch_set_basis_state(qs->prec, qs->d_amp, 1ull << qs->n_lanes, 0, g.stream));
+    g.stats.kernel_launches += 1;
+}
+
 void flush(QStates *qs) {
-    if (qs->queue.empty()) return;
+    if (qs->queue.empty()) {
+        if (qs->d_amp) materialize(qs);
+        return;
+    }
     check_allocated(qs);
     const bool exact = g.opt.exact != 0;
     if (!exact && g.opt.fuse && qs->n_lanes >= min_tile_lanes(qs->prec)) {
@@ -409,6 +425,7 @@ void flush(QStates *qs) {
         else
             flush_tiled<float>(qs);
     } else {
+        materialize(qs);
         for (const Gate &gt : qs->queue) {
             if (!gt.fan.empty()) {
                 /* a phase fan (formed while the tiled path was on): its controlled phases one by one */
@@ -485,6 +502,7 @@ void free_qstates_buffer(QStates *qs) {
         g.pool.release(qs->d_alt);
         qs->d_alt = nullptr;
     }
+    qs->zero_pending = false;
     qs->queue.clear();
 }
 
@@ -801,8 +819,13 @@ int qgb_qproc_reset_qstates(qgb_handle qp, qgb_handle h) {
     check_allocated(qs);
     qs->queue.clear();
     qs->reset_perm();
-    CUDA_CHECK(launch_set_basis_state(qs->prec, qs->d_amp, 1ull << qs->n_lanes, 0, g.stream));
-    g.stats.kernel_launches += 1;
+    if (g.opt.lazy_reset) {
+        qs->zero_pending = true; /* written by the first pass, or by materialize() */
+    } else {
+        qs->zero_pending = false;
+        CUDA_CHECK(launch_set_basis_state(qs->prec, qs->d_amp, 1ull << qs->n_lanes, 0, g.stream));
+        g.stats.kernel_launches += 1;
+    }
     QGB_CATCH
 }
 
@@ -854,6 +877,7 @@ static void join_impl(qgb_handle qp, qgb_handle hdst, const qgb_handle *src_list
         index_offset >= ((int64_t)1 << n_total_lanes))
         fail(QGB_ERR_INVALID, "join: bad shard offset.");
     dst->queue.clear();
+    dst->zero_pending = false; /* every amplitude of the product is written */
     CUDA_CHECK(launch_join(dst->prec, dst->d_amp, dst->n_lanes, shift, (uint64_t)index_offset, jp, g.stream));
     g.stats.kernel_launches += 1;
     /* the product keeps every source's array as it is: source k's lane l (its index bit perm[l])
@@ -1123,6 +1147,7 @@ int qgb_qproc_decohere_and_separate(qgb_handle qp, int value, double prob, qgb_h
     flush(qs);
     qs0->queue.clear();
     qs1->queue.clear();
+    qs0->zero_pending = qs1->zero_pending = false; /* both are written in full below */
     const double norm = (value == 0) ? 1. / std::sqrt(prob) : 1. / std::sqrt(1. - prob);
     const int p = qs->phys(lane);
     CUDA_CHECK(launch_decohere_separate(qs->prec, qs0->d_amp, qs->d_amp, qs->n_lanes, p, value ? 1 : 0,
@@ -1694,6 +1719,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "merge") g.opt.merge = value;
     else if (k == "fans") g.opt.fans = value;
     else if (k == "fan_cost") g.opt.fan_cost = value;
+    else if (k == "lazy_reset") g.opt.lazy_reset = value;
     else if (k == "exact") g.opt.exact = value;
     else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
     else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;

@@ -37,9 +37,12 @@ struct GatherParams {
 /* ---- gates ----------------------------------------------------------------------- */
 /* the fused gate pass, TMA tensor-map staging (kernels_tma.cu); needs prog.n_groups >= 1;
  * n_buf = 2 or 3 tile buffers per CTA; min_ctas = resident CTAs per SM the register budget is
- * set for (3: 80 registers per thread, 2: up to 128) */
+ * set for (3: 80 registers per thread, 2: up to 128); zero_input = 1: the array has not been
+ * written since the state was reset to |0...0> — the pass reads nothing and starts every tile
+ * from that state (half the traffic of the first pass, and no initialisation sweep before it) */
 template <typename real>
-cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf, int min_ctas, cudaStream_t stream);
+cudaError_t launch_tma_pass(const PassProgram<real> &prog, void *amp, int n_buf, int min_ctas, cudaStream_t stream,
+                            int zero_input = 0);
 /* shared memory of one CTA: n_buf tiles, the matrices of n_ops ops, n_stages thread tables */
 size_t tma_pass_smem_bytes(int prec, int T, int K, int n_stages, int n_buf, int n_ops, int n_fans);
 cudaError_t tma_pass_configure(int max_smem_optin, int sm_count);

@@ -58,6 +58,8 @@ struct TmaGeometry {
                                      /* low fan_lo bits of the tile number and by the rest; nullptr when */
                                      /* no fan of the pass has a term outside the tile                   */
     int32_t fan_lo, fan_hi;
+    int32_t zero_input;              /* 1: the state is |0...0> and has not been written yet: no tile is */
+                                     /* loaded, the first stage starts from zeros (amplitude 0 = 1)      */
     int32_t debug_mode;              /* measurement only (option debug_pass_mode): 1 = the stages   */
                                      /* load and store their registers but skip the ops, 2 = no     */
                                      /* stages at all (the tile only travels in and out)             */
@@ -680,13 +682,17 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         if (producer) {
             if (tid == nthr) { /* one lane drives the TMA unit */
                 uint64_t t_load = blockIdx.x;
-                for (int j = 0; j < NBUF && t_load < n_tiles; ++j, t_load += stride) issue_load(t_load, j);
+                for (int j = 0; j < NBUF && t_load < n_tiles && !geo.zero_input; ++j, t_load += stride) issue_load(t_load, j);
+                for (int j = 0; j < NBUF && geo.zero_input; ++j) mbar_arrive(&full[j]); /* nothing to load: the buffers are free */
                 int pb = 0;
                 uint32_t pparity = 0;
                 for (uint64_t t = blockIdx.x; t < n_tiles; t += stride) {
                     mbar_wait(&done[pb], pparity); /* the consumers are through with tile t */
                     issue_store(t, pb);
-                    if (t_load < n_tiles) {
+                    if (geo.zero_input) {
+                        bulk_wait_read<0>(); /* the store has drained the buffer: the consumers may refill it */
+                        mbar_arrive(&full[pb]);
+                    } else if (t_load < n_tiles) {
                         bulk_wait_read<0>(); /* the store has drained the buffer: refill it */
                         issue_load(t_load, pb);
                         t_load += stride;
@@ -702,7 +708,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         }
     } else {
         /* prologue: the first tile */
-        if (tid == 0 && blockIdx.x < n_tiles) issue_load(blockIdx.x, 0);
+        if (tid == 0 && blockIdx.x < n_tiles && !geo.zero_input) issue_load(blockIdx.x, 0);
     }
 
     int b = 0;            /* buffer of the tile being worked on */
@@ -724,7 +730,7 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             const uint64_t tn = t + stride;
             if (tn < n_tiles) {
                 bulk_wait_read<NBUF - 2>();
-                issue_load(tn, b + 1 == NBUF ? 0 : b + 1);
+                if (!geo.zero_input) issue_load(tn, b + 1 == NBUF ? 0 : b + 1);
             }
         }
         /* index of the tile's origin -> the ops this tile skips (controls outside the tile) and
@@ -744,9 +750,10 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
         }
 
         PH_MARK(ph_tail);
-        mbar_wait(&full[b], parity);
+        if (WS || !geo.zero_input) mbar_wait(&full[b], parity);
         PH_MARK(ph_wait);
         unsigned char *buf = tiles + (size_t)b * tile_bytes;
+        bool fresh = geo.zero_input != 0; /* the tile is |0...0>'s: zeros, amplitude 0 of the state = 1 */
 
         for (int s = 0; s < prog.n_stages && geo.debug_mode < 2; ++s) {
             const Stage &st = prog.stage[s];
@@ -762,6 +769,12 @@ tma_pass_kernel(const __grid_constant__ PassProgram<real> prog, const __grid_con
             cplx a[1 << K];
 #pragma unroll
             for (int r = 0; r < (1 << K); ++r) a[r] = *reinterpret_cast<const cplx *>(buf + QGB_SLOT(sbyte, r));
+            if (fresh) { /* (uniform) the first stage of a tile of a state that was never written */
+#pragma unroll
+                for (int r = 0; r < (1 << K); ++r) a[r].x = (real)0, a[r].y = (real)0;
+                if (t == 0 && tid == 0) a[0].x = (real)1; /* thread 0 holds tile element 0 in register 0 */
+                fresh = false;
+            }
             PH_MARK(ph_load);
 
             if (geo.debug_mode == 0) {
@@ -925,6 +938,7 @@ cudaError_t encode_map(const PassProgram<real> &prog, void *amp, CUtensorMap *ma
     geo->debug_mode = g_tma_debug_mode;
     geo->fan_tiles = nullptr;
     geo->fan_lo = geo->fan_hi = 0;
+    geo->zero_input = 0;
     for (int d = 0; d < QGB_MAX_GROUPS; ++d) {
         if (d < prog.n_groups) {
             const int s = prog.grp_start[d], t = prog.grp_t[d], r = prog.grp_r[d];
@@ -990,13 +1004,14 @@ cudaError_t launch_tma_variant(const PassProgram<real> &prog, const CUtensorMap 
 
 template <typename real, int K>
 cudaError_t launch_tma_by_shape(const PassProgram<real> &prog, void *amp, int prec, int n_buf, int min_ctas,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, int zero_input) {
     cudaError_t rc = resolve_encode();
     if (rc != cudaSuccess) return rc;
     CUtensorMap map;
     TmaGeometry geo;
     rc = encode_map<real>(prog, amp, &map, &geo);
     if (rc != cudaSuccess) return rc;
+    geo.zero_input = zero_input ? 1 : 0;
     {
         int n_out_terms = 0;
         for (int f = 0; f < prog.n_fans; ++f) n_out_terms += prog.fan[f].n_out;
@@ -1103,22 +1118,22 @@ cudaError_t tma_pass_configure(int max_smem_optin, int sm_count) {
 #ifdef QGB_TMA_F64
 template <>
 cudaError_t launch_tma_pass<double>(const PassProgram<double> &prog, void *amp, int n_buf, int min_ctas,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, int zero_input) {
     if ((prog.K != 3 && prog.K != 4) || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
         return cudaErrorInvalidValue;
     /* 4 register bits: 16 complex128 per thread, CTAs of half as many threads (up to 128 registers) */
-    if (prog.K == 4) return launch_tma_by_shape<double, 4>(prog, amp, 1, n_buf >= 3 ? 3 : 2, 2, stream);
-    return launch_tma_by_shape<double, 3>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream);
+    if (prog.K == 4) return launch_tma_by_shape<double, 4>(prog, amp, 1, n_buf >= 3 ? 3 : 2, 2, stream, zero_input);
+    return launch_tma_by_shape<double, 3>(prog, amp, 1, n_buf >= 3 ? 3 : 2, min_ctas, stream, zero_input);
 }
 #endif
 
 #ifdef QGB_TMA_F32
 template <>
 cudaError_t launch_tma_pass<float>(const PassProgram<float> &prog, void *amp, int n_buf, int min_ctas,
-                                   cudaStream_t stream) {
+                                   cudaStream_t stream, int zero_input) {
     if (prog.K != QGB_K32 || prog.T < prog.K || prog.T - prog.K > 10 || prog.n_groups < 1 || prog.n_ops > 32)
         return cudaErrorInvalidValue;
-    return launch_tma_by_shape<float, QGB_K32>(prog, amp, 2, n_buf >= 3 ? 3 : 2, min_ctas, stream);
+    return launch_tma_by_shape<float, QGB_K32>(prog, amp, 2, n_buf >= 3 ? 3 : 2, min_ctas, stream, zero_input);
 }
 #endif
 
