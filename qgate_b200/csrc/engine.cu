@@ -594,11 +594,32 @@ double *device_prob_array(int prec, const int *lane_tables, const int *n_per, co
     return cur;
 }
 
-/* device -> caller's (pageable) host buffer through two pinned staging buffers */
+/* device -> caller's (pageable) host buffer.  Small results go directly; large ones (a 2^30-entry
+ * probability array is 8 GiB) travel through the two pinned staging buffers, the host memcpy of chunk
+ * i overlapping the DMA of chunk i + 1 (a pageable cudaMemcpy stages through a small driver buffer
+ * and runs at a fraction of the link rate). */
 void copy_to_host(void *dst, const void *d_src, size_t bytes) {
-    CUDA_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
-    stream_sync();
     g.stats.d2h_bytes += (int64_t)bytes;
+    if (bytes <= (size_t(1) << 20) || !g.h_stage[0] || !g.h_stage[1]) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+        stream_sync();
+        return;
+    }
+    const size_t chunk = g.stage_bytes;
+    const size_t n_chunks = (bytes + chunk - 1) / chunk;
+    auto issue = [&](size_t i) {
+        const size_t off = i * chunk, n = std::min(chunk, bytes - off);
+        CUDA_CHECK(cudaMemcpyAsync(g.h_stage[i & 1], static_cast<const char *>(d_src) + off, n, cudaMemcpyDeviceToHost,
+                                   g.stream));
+        CUDA_CHECK(cudaEventRecord(g.stage_done[i & 1], g.stream));
+    };
+    issue(0);
+    for (size_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) issue(i + 1); /* (buffer (i + 1) & 1 was drained by the memcpy of chunk i - 1) */
+        CUDA_CHECK(cudaEventSynchronize(g.stage_done[i & 1]));
+        const size_t off = i * chunk, n = std::min(chunk, bytes - off);
+        std::memcpy(static_cast<char *>(dst) + off, g.h_stage[i & 1], n);
+    }
 }
 
 } // namespace

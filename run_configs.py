@@ -183,7 +183,7 @@ def run_qft(args, torch, world, rank):
     want = amp * np.exp(2j * np.pi * np.asarray(phase, np.float64) / float(1 << n))
     err = float(np.abs(got - want).max() / amp)
     p0_err = float(np.abs(np.array(p0) - 0.5).max())
-    ok = err < tol * (4 if dtype is np.float32 else 1) and p0_err < tol
+    ok = err < tol and p0_err < tol
     sim.terminate()
     return {'config': 'qft', 'qubits': n, 'dtype': args.dtype, 'gates': len(ops),
             'state_bytes': (16 if dtype is np.float64 else 8) << n, 'run_s': t_run,

@@ -379,7 +379,7 @@ def test_large_state_properties(cuda_runtime, dtype, n):
     xr = (1 << (n - 1)) + (1 << (n - 3))
     phase = (ks * xr) % (1 << n)
     want = amp * np.exp(2j * np.pi * phase.astype(np.float64) / float(1 << n))
-    assert np.abs(got - want).max() < tol * amp * (4 if dtype is np.float32 else 1)
+    assert np.abs(got - want).max() < tol * amp
     for qr in (q[0], q[5], q[n // 2], q[n - 1]):
         assert abs(sim.qubits.calc_probability(qr) - 0.5) < (1e-12 if dtype is np.float64 else 1e-5)
     # inverse: all gates adjointed in reverse order
@@ -390,8 +390,8 @@ def test_large_state_properties(cuda_runtime, dtype, n):
             inverse.append(S.ctrl(q[j]).U1(-math.pi / float(1 << (j - i)))(q[i]))
     sim.run(list(reversed(inverse)))
     head = sim.qubits.states[:8]
-    assert abs(abs(head[5]) - 1.) < (1e-11 if dtype is np.float64 else 2e-5)
-    assert np.abs(np.delete(head, 5)).max() < (1e-11 if dtype is np.float64 else 2e-5)
+    assert abs(abs(head[5]) - 1.) < tol
+    assert np.abs(np.delete(head, 5)).max() < tol
     sim.terminate()
 
 
