@@ -297,6 +297,9 @@ def device_leg(args, dtype_name, n, gates, runtime, api, torch, dist, distribute
     proc = qstates.processor
     proc.initialize_qubit_states(qstates, n)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # this leg times the device alone: every gate is queued BEFORE the first event, so the engine must not
+    # start launching passes while the queue fills (its default; the e2e leg below runs with the default)
+    api.set_option('queue_stream', 0)
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,6 +346,7 @@ def device_leg(args, dtype_name, n, gates, runtime, api, torch, dist, distribute
     exch_ms = runtime.ctx.exchange_ms() if distributed else 0.
     dstats = dict(runtime.ctx.stats) if distributed else None
     qstates.delete()
+    api.set_option('queue_stream', 1)
     del qstates, proc
     n_local = n - int(round(math.log2(max(1, int(os.environ.get('WORLD_SIZE', '1'))))))
     tile_passes = stats['tile_passes']

@@ -221,6 +221,11 @@ struct Options {
     int64_t fans = 1; /* controlled phases that share a lane merge into one phase fan (program.h OP_FAN) */
     int64_t fan_cost = 2;
     int64_t lazy_reset = 1; /* |0...0> is produced by the first fused pass instead of a sweep of its own */
+    /* streaming: once a queue holds stream_hi (merged) gates, passes are planned and launched until
+     * stream_keep are left — the device works while the caller is still submitting (the reference front
+     * end spends ~5 us per gate in Python).  The pass sequence is the one a single flush at the end
+     * plans (379 passes either way on the bench circuit: the planner looks at the front of the queue). */
+    int64_t queue_stream = 1, stream_hi = 512, stream_keep = 256;
     /* 1: every gate as submitted, one kernel each, in the reference CPU runtime's arithmetic
      * operation by operation (CPUQubitProcessor.cpp:316-324): amplitudes bit-identical to
      * qgate.simulator.cpu's.  A verification mode (one state sweep per gate), off by default. */
@@ -336,7 +341,7 @@ int default_max_cost(bool fp32, bool shear) {
 }
 
 template <typename real>
-void flush_tiled(QStates *qs) {
+void flush_tiled(QStates *qs, size_t down_to = 0) {
     const bool fp32 = sizeof(real) == 4;
     PlanConfig cfg;
     cfg.fp32 = fp32;
@@ -382,7 +387,7 @@ void flush_tiled(QStates *qs) {
     cfg.fan_cost = (int)std::max<int64_t>(1, g.opt.fan_cost);
     static PassProgram<real> prog; /* ~11 KB, passed by value to the kernel */
     PlanStats st;
-    while (!qs->queue.empty()) {
+    while (qs->queue.size() > down_to) {
         plan_pass<real>(qs->queue, qs->n_lanes, cfg, prog, st);
         if (st.gates_in_pass <= 0) fail(QGB_ERR_RUNTIME, "planner made no progress.");
         if (prog.n_groups < 1) fail(QGB_ERR_RUNTIME, "planner produced a tile no tensor map describes.");
@@ -489,6 +494,13 @@ void submit_queued(QStates *qs, const Gate &gt, int n_ctrl) {
     g.stats.gates_submitted += 1;
     g.stats.gate_amp_updates += (int64_t)1 << (qs->n_lanes - n_ctrl);
     if ((int64_t)qs->queue.size() >= g.opt.queue_limit) flush(qs);
+    if (tiled && g.opt.queue_stream && g.opt.stream_hi > 0 && (int64_t)qs->queue.size() >= g.opt.stream_hi) {
+        const size_t keep = (size_t)std::max<int64_t>(0, std::min(g.opt.stream_keep, g.opt.stream_hi - 1));
+        if (qs->prec == QGB_PREC_FP64)
+            flush_tiled<double>(qs, keep);
+        else
+            flush_tiled<float>(qs, keep);
+    }
 }
 
 void stream_sync() { CUDA_CHECK(cudaStreamSynchronize(g.stream)); }
@@ -1741,6 +1753,9 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "fans") g.opt.fans = value;
     else if (k == "fan_cost") g.opt.fan_cost = value;
     else if (k == "lazy_reset") g.opt.lazy_reset = value;
+    else if (k == "queue_stream") g.opt.queue_stream = value;
+    else if (k == "stream_hi") g.opt.stream_hi = value;
+    else if (k == "stream_keep") g.opt.stream_keep = value;
     else if (k == "exact") g.opt.exact = value;
     else if (k == "tile_lanes_fp64") g.opt.tile_lanes_fp64 = value;
     else if (k == "tile_lanes_fp32") g.opt.tile_lanes_fp32 = value;

@@ -31,7 +31,8 @@ def default_options(cuda_runtime):
                         ('low_lanes_fp64', 0), ('low_lanes_fp32', 0), ('max_gates_per_pass', 112), ('max_cost', 0),
                         ('tma_buffers', 0), ('reg_bits_fp64', 4), ('ctas_per_sm', 0), ('tma_ws', 0),
                         ('warp_local', 0), ('shear_fp64', 1), ('shear_fp32', 1), ('exact', 0), ('l2_hint', 0),
-                        ('debug_pass_mode', 0)):
+                        ('debug_pass_mode', 0), ('queue_stream', 1), ('stream_hi', 512), ('stream_keep', 256),
+                        ('lazy_reset', 1)):
         api.set_option(name, value)
     yield
 
@@ -340,6 +341,11 @@ def test_fused_equals_unfused_and_tile_shapes(cuda_runtime, dtype):
     for t in (k + 6, k + 7, k + 8, k + 9):           # warp-local stage transitions
         shapes.append({'fuse': 1, 'warp_local': 1, lanes: t, low: 0})
     shapes.append({'fuse': 1, 'warp_local': 0, lanes: k + 6, low: 0})
+    # streaming (passes launched while the queue fills) at tiny thresholds, off, and the eager |0...0> sweep
+    shapes.append(dict(fuse=1, queue_stream=1, stream_hi=8, stream_keep=3))
+    shapes.append(dict(fuse=1, queue_stream=1, stream_hi=2, stream_keep=0))
+    shapes.append(dict(fuse=1, queue_stream=0, stream_hi=512, stream_keep=256, lazy_reset=0))
+    shapes.append(dict(fuse=1, queue_stream=1, lazy_reset=1))
     if dtype is np.float64:
         for t in (8, 9, 11, 12):
             for shear in (0, 1):
