@@ -31,6 +31,7 @@ copy and does the same work on it, so no communication is needed for them either
 """
 import ctypes as C
 import math
+import os
 import weakref
 
 import numpy as np
@@ -416,11 +417,24 @@ class DistQubitProcessor:
             self.api.check(rc)
         return mat
 
+    # Streaming: every STREAM submitted gates, whatever needs no exchange goes on to the local engine
+    # (which launches passes as its own queue fills), so the device works while the front end is still
+    # dispatching; the gates that wait for an exchange stay here, in order.
+    STREAM = int(os.environ.get('QGB_DIST_STREAM', '2048'))
+
+    def _submitted(self, qs):
+        qs.n_fresh = getattr(qs, 'n_fresh', 0) + 1
+        if qs.n_fresh >= self.STREAM and qs.g:
+            qs.n_fresh = 0
+            qs.pending = self._apply_unblocked(qs, qs.pending)
+
     def apply_gate(self, gate_type, adjoint, qs, lane):
         qs.pending.append(Gate(self._matrix(gate_type, adjoint), (), lane))
+        self._submitted(qs)
 
     def apply_controlled_gate(self, gate_type, adjoint, qs, ctrl_lanes, target_lane):
         qs.pending.append(Gate(self._matrix(gate_type, adjoint), tuple(ctrl_lanes), target_lane))
+        self._submitted(qs)
 
     def submit_tuples(self, qs, gates):
         """bench.py's compact form: (u3 angles or None, control lane or -1, target lane)."""

@@ -92,6 +92,9 @@ def _worker(rank, world, port, case, dtype_name, prep, queue):
         os.environ['MASTER_ADDR'] = '127.0.0.1'
         os.environ['MASTER_PORT'] = str(port)
         os.environ['QGATE_NUM_WORKERS'] = '1'
+        # world 4 streams the unblocked gates to the local engine every 16 submissions (dist.py
+        # _submitted: 2048 by default, more than these circuits hold), world 2 / 8 run them at the flush
+        os.environ['QGB_DIST_STREAM'] = '16' if world == 4 else '2048'
         import torch
         import torch.distributed as dist
         torch.set_num_threads(1)
