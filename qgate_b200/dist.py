@@ -88,6 +88,9 @@ class Gate:
         self.zmask = z
 
 
+_RETAINED = {}      # library -> {'bases': {mapping base: True}, 'key': shard shape they served}
+
+
 class DistContext:
     def __init__(self, local_module, group=None, exchange='auto', shard_min_lanes=None, push=True):
         if not dist.is_initialized():
@@ -135,17 +138,30 @@ class DistContext:
         # this every fresh simulator pays it per peer and buffer (profiles/r2r).  They are dropped when
         # a sharded state of another size is created (every rank takes that decision alike) and when
         # the runtime shuts down.
-        self.retained = {}           # mapping base -> True, each holding one reference of the engine's
-        self.retained_key = None     # (local lanes, bytes per amplitude) the retained mappings served
+        # (process-wide, like the engine's table of open mappings: bench.py and run_configs.py use
+        # several runtime modules, hence several contexts, one after the other)
+        self._keep = _RETAINED.setdefault(id(self.api.lib), {'bases': {}, 'key': None})
+
+    @property
+    def retained(self):
+        return self._keep['bases']   # mapping base -> True, each holding one reference of the engine's
+
+    @property
+    def retained_key(self):
+        return self._keep['key']     # (local lanes, bytes per amplitude) the retained mappings served
+
+    @retained_key.setter
+    def retained_key(self, key):
+        self._keep['key'] = key
 
     def drop_retained(self):
-        for base in list(self.retained):
+        for base in list(self._keep['bases']):
             try:
                 self.api.call('qgb_ipc_close', base)
             except Exception:
                 pass
-        self.retained = {}
-        self.retained_key = None
+        self._keep['bases'].clear()
+        self._keep['key'] = None
 
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
     def bind_stream(self):

@@ -1,0 +1,19 @@
+#!/bin/bash
+# round-2 GPU session z (4 GPUs, final code): sharded parity over NCCL at world 4, the driver's bench command at N=4
+# (QFT-32 and QFT-35 = 128 GiB shards in its qft sub-record), bench with the in-place exchange.
+mkdir -p gpurun_out
+( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 5 --warmup 3 ) > gpurun_out/r2z_bench_4gpu.json 2> gpurun_out/r2z_bench_4gpu.err; tail -4 gpurun_out/r2z_bench_4gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 3 --warmup 3 --exchange p2p_inplace --no-extras --no-e2e > gpurun_out/r2z_bench_4gpu_inplace.json 2> gpurun_out/r2z_bench_4gpu_inplace.err
+python - <<'PY'
+import json
+for tag in ('r2z_bench_4gpu', 'r2z_bench_4gpu_inplace'):
+    try:
+        d = json.loads(open('gpurun_out/%s.json' % tag).read().strip().splitlines()[-1])
+        r, nv = d['roofline'], d['nvlink']
+        print(tag, 'upd/s %.3e ms/step %.1f frac %.3f passes %.0f | e2e %s | nvlink %s | f32 %s | qft %s' % (
+            d['value'], d['ms_per_step'], r['frac'], r['launches_per_step'], d['e2e'] and '%.3e' % d['e2e']['value'],
+            {k: nv[k] for k in ('exchange', 'exchanges_per_step', 'lanes_per_exchange', 'ms_per_step', 'achieved', 'frac')},
+            d.get('f32') and '%.3e' % d['f32']['value'], d.get('qft')))
+    except Exception as e:
+        print(tag, 'failed', e, open('gpurun_out/%s.err' % tag).read()[-1200:])
+PY
