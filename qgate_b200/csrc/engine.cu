@@ -149,12 +149,28 @@ struct MemPool {
         /* Keep the block for the next qstates of this size class: cudaMalloc + cudaFree of a 16 GiB
          * state vector cost ~0.3 s each (bench.py e2e split), re-use is free and stream-ordered.
          * Big blocks are capped: at most two per size class (a sharded state vector and the spare
-         * buffer of its push exchange) and 136 GiB in total (one 128 GiB shard); an allocation that
-         * fails trims the whole cache and retries (alloc). */
+         * buffer of its push exchange) and 136 GiB in total (one 128 GiB shard).  The block released
+         * last is the likeliest to be asked for again: older blocks of other size classes make room
+         * for it.  An allocation that fails trims the whole cache and retries (alloc). */
         const bool big = c > (size_t(1) << 28);
-        if (big && (cached[c].size() >= 2 || cached_bytes + c > (size_t(136) << 30))) {
+        const size_t cap = size_t(136) << 30;
+        if (big && (cached[c].size() >= 2 || c > cap)) {
             cudaFree(p);
             return;
+        }
+        if (big && cached_bytes + c > cap) {
+            for (auto it2 = cached.rbegin(); it2 != cached.rend() && cached_bytes + c > cap; ++it2) { /* largest first */
+                if (it2->first == c) continue;
+                while (!it2->second.empty() && cached_bytes + c > cap) {
+                    cudaFree(it2->second.back());
+                    it2->second.pop_back();
+                    cached_bytes -= it2->first;
+                }
+            }
+            if (cached_bytes + c > cap) {
+                cudaFree(p);
+                return;
+            }
         }
         cached[c].push_back(p);
         cached_bytes += c;

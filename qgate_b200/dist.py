@@ -88,9 +88,6 @@ class Gate:
         self.zmask = z
 
 
-_RETAINED = {}      # library -> {'bases': {mapping base: True}, 'key': shard shape they served}
-
-
 class DistContext:
     def __init__(self, local_module, group=None, exchange='auto', shard_min_lanes=None, push=True):
         if not dist.is_initialized():
@@ -132,36 +129,6 @@ class DistContext:
         self.timing = False          # bench.py: CUDA events around every exchange
         self._exchange_events = []
         self._barrier_buf = None
-        # IPC mappings of the peers' shards outlive the qstates that opened them: the engine's pool
-        # hands the next state vector of the same size the same blocks, whose handles then hit these
-        # mappings again.  Mapping a peer's 128 GiB shard costs ~0.25 s, a 16 GiB one 30 ms: without
-        # this every fresh simulator pays it per peer and buffer (profiles/r2r).  They are dropped when
-        # a sharded state of another size is created (every rank takes that decision alike) and when
-        # the runtime shuts down.
-        # (process-wide, like the engine's table of open mappings: bench.py and run_configs.py use
-        # several runtime modules, hence several contexts, one after the other)
-        self._keep = _RETAINED.setdefault(id(self.api.lib), {'bases': {}, 'key': None})
-
-    @property
-    def retained(self):
-        return self._keep['bases']   # mapping base -> True, each holding one reference of the engine's
-
-    @property
-    def retained_key(self):
-        return self._keep['key']     # (local lanes, bytes per amplitude) the retained mappings served
-
-    @retained_key.setter
-    def retained_key(self, key):
-        self._keep['key'] = key
-
-    def drop_retained(self):
-        for base in list(self._keep['bases']):
-            try:
-                self.api.call('qgb_ipc_close', base)
-            except Exception:
-                pass
-        self._keep['bases'].clear()
-        self._keep['key'] = None
 
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
     def bind_stream(self):
@@ -298,14 +265,11 @@ class DistQubitStates:
 
     def _close_peers(self):
         if self.peers:
-            ctx = self.ctx
-            keep = getattr(self, 'peer_key', None)
+            # (mappings are NOT kept for re-use by the next state vector: a peer that frees a block we
+            # still map would get no memory back, and could not know why — measured on 2 GPUs)
             for base in self.peer_bases:
-                if keep is not None and keep == ctx.retained_key and base not in ctx.retained:
-                    ctx.retained[base] = True          # the reference moves to the context
-                    continue
                 try:
-                    ctx.api.call('qgb_ipc_close', base)
+                    self.ctx.api.call('qgb_ipc_close', base)
                 except Exception:
                     pass
         self.peers = None
@@ -378,17 +342,6 @@ class DistQubitProcessor:
         qs.perm = list(range(n_lanes))
         qs.pending = []
         ctx.bind_stream()
-        if qs.g:
-            key = (n_lanes - qs.g, np.dtype(qs.dtype).itemsize)
-            if ctx.retained and ctx.retained_key != key:
-                # mappings kept for shards of another size pin the peers' freed blocks: close them, on
-                # every rank, before anybody allocates the new shards
-                ctx.drop_retained()
-                ctx.device_barrier()
-                if ctx.on_cuda:
-                    torch.cuda.synchronize()     # (the barrier is stream-ordered; allocation is a host call)
-            ctx.retained_key = key
-            qs.peer_key = key
         self._lp(qs).initialize_qubit_states(qs.local, n_lanes - qs.g)
         qs.reset_lane_states()
 

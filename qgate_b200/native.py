@@ -387,11 +387,6 @@ class RuntimeModule:
             obj.delete()
         if self.initialized:
             self.api.call('qgb_devices_clear')
-            # (the library has just closed every IPC mapping: forget the ones dist.py kept for re-use)
-            import sys
-            dist_module = sys.modules.get(__package__ + '.dist')
-            if dist_module is not None:
-                dist_module._RETAINED.pop(id(self.api.lib), None)
         self.initialized = False
 
     def create_qubit_states(self, dtype):

@@ -3,10 +3,9 @@
 # (QFT-32 and QFT-35 = 128 GiB shards in its qft sub-record), bench with the in-place exchange.
 mkdir -p gpurun_out
 ( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 4 --steps 5 --warmup 3 ) > gpurun_out/r2z_bench_4gpu.json 2> gpurun_out/r2z_bench_4gpu.err; tail -4 gpurun_out/r2z_bench_4gpu.err
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 4 --steps 3 --warmup 3 --exchange p2p_inplace --no-extras --no-e2e > gpurun_out/r2z_bench_4gpu_inplace.json 2> gpurun_out/r2z_bench_4gpu_inplace.err
 python - <<'PY'
 import json
-for tag in ('r2z_bench_4gpu', 'r2z_bench_4gpu_inplace'):
+for tag in ('r2z_bench_4gpu',):
     try:
         d = json.loads(open('gpurun_out/%s.json' % tag).read().strip().splitlines()[-1])
         r, nv = d['roofline'], d['nvlink']
