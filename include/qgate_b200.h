@@ -220,6 +220,10 @@ int qgb_pool_from_prob_array(int prec, const double *prob, int n_lanes,
 /* CUDA IPC: export the allocation behind a qstates (64-byte cudaIpcMemHandle_t + the
  * offset of the array inside it), map / unmap a peer's export in this process. */
 int qgb_qstates_ipc_export(qgb_handle qstates, void *handle64, int64_t *offset);
+/* Frees the cached blocks that were exported through CUDA IPC.  The pool never frees such a block on
+ * its own (a peer that still maps it would keep the memory alive); the sharding layer calls this once
+ * every rank has closed its mappings — before a sharded state vector of another size is created. */
+int qgb_pool_trim_exported(void);
 int qgb_ipc_open(const void *handle64, uint64_t *base_ptr);
 int qgb_ipc_close(uint64_t base_ptr);
 /* in-place exchange of k global lanes with the k local lanes victim_lanes[] (ascending):

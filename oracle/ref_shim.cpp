@@ -673,6 +673,7 @@ int qgb_ipc_close(uint64_t) { return fail(QGB_ERR_RUNTIME, "no CUDA IPC in the C
 int qgb_qstates_exchange_p2p(qgb_handle, const uint64_t *, int, const int *, int) {
     return fail(QGB_ERR_RUNTIME, "no peer-memory exchange in the CPU shim.");
 }
+int qgb_pool_trim_exported(void) { return QGB_OK; }
 int qgb_qstates_ipc_export_alt(qgb_handle, void *, int64_t *) { return fail(QGB_ERR_RUNTIME, "no CUDA IPC in the CPU shim."); }
 int qgb_qstates_exchange_push(qgb_handle, const uint64_t *, int, const int *, int) {
     return fail(QGB_ERR_RUNTIME, "no peer-memory exchange in the CPU shim.");

@@ -99,6 +99,7 @@ SIGNATURES = {
     'qgb_qstates_exchange_p2p': [_h, _hp, _i, _ip, _i],
     'qgb_qstates_ipc_export_alt': [_h, _p, _i64p],
     'qgb_qstates_exchange_push': [_h, _hp, _i, _ip, _i],
+    'qgb_pool_trim_exported': [],
 }
 _NON_STATUS = {
     'qgb_last_error': ([], C.c_char_p),

@@ -93,6 +93,12 @@ struct Error {
 struct MemPool {
     std::map<size_t, std::vector<void *>> cached;
     std::unordered_map<void *, size_t> live;
+    /* blocks other processes may have mapped (CUDA IPC, sharded state vectors): a peer that still maps
+     * a block keeps its memory alive, so freeing it here would give nothing back — and dist.py keeps
+     * its mappings across state vectors because unmapping a used 16 GiB buffer costs ~0.1 s.  Such
+     * blocks are only ever freed by trim_exported(), which dist.py calls after every rank has dropped
+     * its mappings (a sharded state vector of another size is about to be created), and at shutdown. */
+    std::unordered_set<void *> exported;
     size_t live_bytes = 0, cached_bytes = 0;
     int64_t budget = -1; /* memory_store_size preference; -1 = whatever the device has */
 
@@ -102,11 +108,35 @@ struct MemPool {
         return c;
     }
 
-    void trim() {
-        for (auto &kv : cached)
-            for (void *p : kv.second) cudaFree(p);
-        cached.clear();
-        cached_bytes = 0;
+    void trim(bool exported_too = false) {
+        for (auto &kv : cached) {
+            std::vector<void *> kept;
+            for (void *p : kv.second) {
+                if (!exported_too && exported.count(p)) {
+                    kept.push_back(p);
+                    continue;
+                }
+                cudaFree(p);
+                exported.erase(p);
+                cached_bytes -= kv.first;
+            }
+            kv.second.swap(kept);
+        }
+    }
+    void trim_exported() {
+        for (auto &kv : cached) {
+            std::vector<void *> kept;
+            for (void *p : kv.second) {
+                if (!exported.count(p)) {
+                    kept.push_back(p);
+                    continue;
+                }
+                cudaFree(p);
+                exported.erase(p);
+                cached_bytes -= kv.first;
+            }
+            kv.second.swap(kept);
+        }
     }
 
     void *alloc(size_t bytes) {
@@ -154,6 +184,11 @@ struct MemPool {
          * for it.  An allocation that fails trims the whole cache and retries (alloc). */
         const bool big = c > (size_t(1) << 28);
         const size_t cap = size_t(136) << 30;
+        if (exported.count(p)) { /* stays until trim_exported(), see above */
+            cached[c].push_back(p);
+            cached_bytes += c;
+            return;
+        }
         if (big && (cached[c].size() >= 2 || c > cap)) {
             cudaFree(p);
             return;
@@ -161,11 +196,16 @@ struct MemPool {
         if (big && cached_bytes + c > cap) {
             for (auto it2 = cached.rbegin(); it2 != cached.rend() && cached_bytes + c > cap; ++it2) { /* largest first */
                 if (it2->first == c) continue;
-                while (!it2->second.empty() && cached_bytes + c > cap) {
-                    cudaFree(it2->second.back());
-                    it2->second.pop_back();
+                std::vector<void *> kept;
+                for (void *q : it2->second) {
+                    if (exported.count(q) || cached_bytes + c <= cap) {
+                        kept.push_back(q);
+                        continue;
+                    }
+                    cudaFree(q);
                     cached_bytes -= it2->first;
                 }
+                it2->second.swap(kept);
             }
             if (cached_bytes + c > cap) {
                 cudaFree(p);
@@ -177,9 +217,12 @@ struct MemPool {
     }
 
     void clear() {
-        trim();
+        trim(true);
+        cached.clear();
+        cached_bytes = 0;
         for (auto &kv : live) cudaFree(kv.first);
         live.clear();
+        exported.clear();
         live_bytes = 0;
     }
 };
@@ -1046,6 +1089,7 @@ int qgb_qstates_ipc_export(qgb_handle h, void *handle64, int64_t *offset) {
     }
     cudaIpcMemHandle_t hd;
     CUDA_CHECK(cudaIpcGetMemHandle(&hd, base));
+    g.pool.exported.insert(qs->d_amp); /* (pool blocks are whole allocations: d_amp is what release() sees) */
     std::memcpy(handle64, &hd, sizeof(hd));
     if (offset) *offset = (int64_t)(reinterpret_cast<char *>(qs->d_amp) - reinterpret_cast<char *>(base));
     QGB_CATCH
@@ -1061,6 +1105,13 @@ int qgb_qstates_ipc_export_alt(qgb_handle h, void *handle64, int64_t *offset) {
     const int rc = qgb_qstates_ipc_export(h, handle64, offset);
     std::swap(qs->d_amp, qs->d_alt);
     if (rc != QGB_OK) return rc;
+    QGB_CATCH
+}
+
+int qgb_pool_trim_exported(void) {
+    QGB_TRY
+    require_init();
+    g.pool.trim_exported();
     QGB_CATCH
 }
 

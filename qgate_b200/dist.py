@@ -88,6 +88,17 @@ class Gate:
         self.zmask = z
 
 
+# IPC mappings of the peers' shards outlive the qstates that opened them (per library, process-wide:
+# bench.py and run_configs.py go through several runtime modules): unmapping a 16 GiB buffer that has
+# been written through costs ~0.1 s (profiles/r2zd), and the engine's pool hands the next state vector
+# of the same size the same blocks, whose handles then hit the kept mappings.  The other half of the
+# contract is in the engine: a block that was exported is never freed behind the peers' backs
+# (engine.cu MemPool::exported).  When a sharded state vector of ANOTHER size is created, every rank
+# (they all take this decision alike) closes its kept mappings, the ranks meet, and only then the
+# exported blocks are freed (qgb_pool_trim_exported) and the new shards allocated.
+_RETAINED = {}      # id(library) -> {'bases': {mapping base: True}, 'key': shard shape they serve}
+
+
 class DistContext:
     def __init__(self, local_module, group=None, exchange='auto', shard_min_lanes=None, push=True):
         if not dist.is_initialized():
@@ -129,6 +140,16 @@ class DistContext:
         self.timing = False          # bench.py: CUDA events around every exchange
         self._exchange_events = []
         self._barrier_buf = None
+        self._keep = _RETAINED.setdefault(id(self.api.lib), {'bases': {}, 'key': None})
+
+    def drop_retained(self):
+        for base in list(self._keep['bases']):
+            try:
+                self.api.call('qgb_ipc_close', base)
+            except Exception:
+                pass
+        self._keep['bases'].clear()
+        self._keep['key'] = None
 
     # -- stream plumbing: NCCL work and the engine's kernels share one stream ----------------
     def bind_stream(self):
@@ -265,9 +286,12 @@ class DistQubitStates:
 
     def _close_peers(self):
         if self.peers:
-            # (mappings are NOT kept for re-use by the next state vector: a peer that frees a block we
-            # still map would get no memory back, and could not know why — measured on 2 GPUs)
+            keep = self.ctx._keep
+            mine = getattr(self, 'peer_key', None)
             for base in self.peer_bases:
+                if self.ctx.on_cuda and mine is not None and mine == keep['key'] and base not in keep['bases']:
+                    keep['bases'][base] = True      # the reference moves to the process-wide table
+                    continue
                 try:
                     self.ctx.api.call('qgb_ipc_close', base)
                 except Exception:
@@ -342,6 +366,18 @@ class DistQubitProcessor:
         qs.perm = list(range(n_lanes))
         qs.pending = []
         ctx.bind_stream()
+        if qs.g and ctx.on_cuda:
+            key = (n_lanes - qs.g, np.dtype(qs.dtype).itemsize)
+            keep = ctx._keep
+            if keep['key'] is not None and keep['key'] != key:
+                # shards of another size: the kept mappings go, on every rank, and only when all of
+                # them are gone are the blocks behind them freed (see _RETAINED)
+                ctx.drop_retained()
+                ctx.device_barrier()
+                torch.cuda.synchronize()         # (the barrier is stream-ordered; freeing is a host call)
+                self.api.call('qgb_pool_trim_exported')
+            keep['key'] = key
+            qs.peer_key = key
         self._lp(qs).initialize_qubit_states(qs.local, n_lanes - qs.g)
         qs.reset_lane_states()
 

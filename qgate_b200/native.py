@@ -387,6 +387,14 @@ class RuntimeModule:
             obj.delete()
         if self.initialized:
             self.api.call('qgb_devices_clear')
+            # (the library has just closed every IPC mapping: forget the ones dist.py kept for re-use)
+            import sys
+            dist_module = sys.modules.get(__package__ + '.dist')
+            if dist_module is not None:
+                kept = dist_module._RETAINED.get(id(self.api.lib))
+                if kept is not None:
+                    kept['bases'].clear()
+                    kept['key'] = None
         self.initialized = False
 
     def create_qubit_states(self, dtype):

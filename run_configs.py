@@ -69,11 +69,17 @@ def run_grover(args, torch, world, rank):
     q, ops = circuits.grover(S, n, k, marked)
     sim = qgate_b200.simulator.cuda(dtype=dtype, circuit_prep=qgate_b200.prefs.one_static)
     drain(torch, world)
-    t0 = time.perf_counter()
-    sim.run(ops)
-    sim.qubits.set_ordering(q)
-    drain(torch, world)
-    t_run = time.perf_counter() - t0
+    import gc
+    gc.collect()           # (a full collection of the caller's garbage inside a 50 ms run is a 100 ms outlier)
+    gc.disable()
+    try:
+        t0 = time.perf_counter()
+        sim.run(ops)
+        sim.qubits.set_ordering(q)
+        drain(torch, world)
+        t_run = time.perf_counter() - t0
+    finally:
+        gc.enable()
     theta = math.asin(2. ** (-n / 2.))
     p_want = math.sin((2 * k + 1) * theta) ** 2
     p_got = float(sim.qubits.prob[marked])
