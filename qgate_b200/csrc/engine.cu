@@ -99,6 +99,7 @@ struct MemPool {
      * blocks are only ever freed by trim_exported(), which dist.py calls after every rank has dropped
      * its mappings (a sharded state vector of another size is about to be created), and at shutdown. */
     std::unordered_set<void *> exported;
+    bool pin_exported = false; /* option pin_exported: set by dist.py when it keeps its mappings */
     size_t live_bytes = 0, cached_bytes = 0;
     int64_t budget = -1; /* memory_store_size preference; -1 = whatever the device has */
 
@@ -112,7 +113,7 @@ struct MemPool {
         for (auto &kv : cached) {
             std::vector<void *> kept;
             for (void *p : kv.second) {
-                if (!exported_too && exported.count(p)) {
+                if (!exported_too && pin_exported && exported.count(p)) {
                     kept.push_back(p);
                     continue;
                 }
@@ -184,13 +185,14 @@ struct MemPool {
          * for it.  An allocation that fails trims the whole cache and retries (alloc). */
         const bool big = c > (size_t(1) << 28);
         const size_t cap = size_t(136) << 30;
-        if (exported.count(p)) { /* stays until trim_exported(), see above */
+        if (pin_exported && exported.count(p)) { /* stays until trim_exported(), see above */
             cached[c].push_back(p);
             cached_bytes += c;
             return;
         }
         if (big && (cached[c].size() >= 2 || c > cap)) {
             cudaFree(p);
+            exported.erase(p);
             return;
         }
         if (big && cached_bytes + c > cap) {
@@ -198,17 +200,19 @@ struct MemPool {
                 if (it2->first == c) continue;
                 std::vector<void *> kept;
                 for (void *q : it2->second) {
-                    if (exported.count(q) || cached_bytes + c <= cap) {
+                    if ((pin_exported && exported.count(q)) || cached_bytes + c <= cap) {
                         kept.push_back(q);
                         continue;
                     }
                     cudaFree(q);
+                    exported.erase(q);
                     cached_bytes -= it2->first;
                 }
                 it2->second.swap(kept);
             }
             if (cached_bytes + c > cap) {
                 cudaFree(p);
+                exported.erase(p);
                 return;
             }
         }
@@ -1820,6 +1824,7 @@ int qgb_set_option(const char *name, int64_t value) {
     else if (k == "fans") g.opt.fans = value;
     else if (k == "fan_cost") g.opt.fan_cost = value;
     else if (k == "lazy_reset") g.opt.lazy_reset = value;
+    else if (k == "pin_exported") g.pool.pin_exported = value != 0;
     else if (k == "queue_stream") g.opt.queue_stream = value;
     else if (k == "stream_hi") g.opt.stream_hi = value;
     else if (k == "stream_keep") g.opt.stream_keep = value;

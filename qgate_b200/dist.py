@@ -141,6 +141,11 @@ class DistContext:
         self._exchange_events = []
         self._barrier_buf = None
         self._keep = _RETAINED.setdefault(id(self.api.lib), {'bases': {}, 'key': None})
+        # kept mappings need the engine to pin exported blocks; both only in the one-rank-per-GPU NCCL
+        # configuration (ranks sharing a GPU over gloo are a test vehicle: they unmap at once, as before)
+        self.keep_mappings = self.comm_cuda
+        if self.keep_mappings:
+            self.api.set_option('pin_exported', 1)
 
     def drop_retained(self):
         for base in list(self._keep['bases']):
@@ -289,7 +294,7 @@ class DistQubitStates:
             keep = self.ctx._keep
             mine = getattr(self, 'peer_key', None)
             for base in self.peer_bases:
-                if self.ctx.on_cuda and mine is not None and mine == keep['key'] and base not in keep['bases']:
+                if self.ctx.keep_mappings and mine is not None and mine == keep['key'] and base not in keep['bases']:
                     keep['bases'][base] = True      # the reference moves to the process-wide table
                     continue
                 try:
@@ -366,7 +371,7 @@ class DistQubitProcessor:
         qs.perm = list(range(n_lanes))
         qs.pending = []
         ctx.bind_stream()
-        if qs.g and ctx.on_cuda:
+        if qs.g and ctx.keep_mappings:
             key = (n_lanes - qs.g, np.dtype(qs.dtype).itemsize)
             keep = ctx._keep
             if keep['key'] is not None and keep['key'] != key:
