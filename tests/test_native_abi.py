@@ -87,3 +87,19 @@ def test_planner_against_tile_kernel_emulator(tmp_path):
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stdout[-4000:]
     assert 'ALL OK' in out.stdout
+
+
+def test_memory_pool_against_a_mock_allocator(tmp_path):
+    """engine.cu's MemPool (size classes, caps, eviction, trim-and-retry, the no-free contract for blocks
+    exported through CUDA IPC) compiled as it stands in the product against a mock cudaMalloc / cudaFree
+    with a fixed capacity: tests/native/pool_emul.cpp."""
+    src = open(os.path.join(REPO, 'qgate_b200', 'csrc', 'engine.cu')).read()
+    begin, end = src.index('struct MemPool {'), src.index('/* ---- objects')
+    with open(str(tmp_path / 'pool_extract.h'), 'w') as f:
+        f.write(src[begin:end])
+    exe = str(tmp_path / 'pool_emul')
+    subprocess.check_call(['g++', '-std=c++17', '-O1', '-I' + str(tmp_path),
+                           os.path.join(REPO, 'tests', 'native', 'pool_emul.cpp'), '-o', exe])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout[-4000:]
+    assert 'ALL OK' in out.stdout
