@@ -803,3 +803,55 @@ def test_phase_fans_on_the_one_kernel_per_gate_path(cuda_runtime, dtype):
         want = want * np.where(((idx >> i) & 1) & ((idx >> j) & 1), np.exp(1j * phi), 1.)
     for amp in outs:
         assert cases.rel_err(amp, want) < cases.TOL[dtype]
+
+
+def _product_state_case(runtime, dtype):
+    """44 qregs that never get entangled: dynamic qubit grouping keeps 44 one-lane qstates (the reference
+    has no cap on their number, qubits_handler.py; ADVICE round 1: the engine's readout used to stop at 40)."""
+    n = 44
+    q = S.new_qregs(n)
+    angles = [0.2 + 0.07 * i for i in range(n)]
+    ops = [S.Ry(a)(x) for a, x in zip(angles, q)] + [S.Rz(0.3 * (i % 5))(x) for i, x in enumerate(q)]
+    sim = cases.make_sim(runtime, dtype, 'dynamic')
+    sim.run(ops)
+    sim.qubits.set_ordering(q)
+    assert len(sim.qubits.qstates_list) == n
+    c = np.cos(np.array(angles) / 2.)
+    s = np.sin(np.array(angles) / 2.)
+    ph = np.exp(1j * 0.3 * (np.arange(n) % 5))          # Rz = diag(1, e^{i phi}) up to the reference's convention
+    rz = cases_rz_diag()
+
+    def amplitude(idx):
+        val = 1. + 0j
+        for i in range(n):
+            bit = (idx >> i) & 1
+            val *= (s[i] * rz[1](0.3 * (i % 5)) if bit else c[i] * rz[0](0.3 * (i % 5)))
+        return val
+    picks = [0, 1, 5, (1 << 43) + 12345, (1 << 44) - 1, 0x5A5A5A5A5A5]
+    tol = cases.TOL[dtype] * 10 if dtype is np.float32 else 1e-12
+    for idx in picks:
+        got = sim.qubits.states[idx]
+        assert abs(got - amplitude(idx)) < tol, (idx, got, amplitude(idx))
+    head = sim.qubits.states[:64]
+    assert np.abs(head - np.array([amplitude(i) for i in range(64)])).max() < tol
+    strided = sim.qubits.states[7:(1 << 44):(1 << 40) + 3]
+    want = np.array([amplitude(i) for i in range(7, 1 << 44, (1 << 40) + 3)])
+    assert strided.shape == want.shape and np.abs(strided - want).max() < tol
+    probs = sim.qubits.prob[:16]
+    assert np.abs(probs - np.abs(np.array([amplitude(i) for i in range(16)])) ** 2).max() < tol
+    for i in (0, 17, 43):
+        assert abs(sim.qubits.calc_probability(q[i]) - c[i] ** 2) < (1e-12 if dtype is np.float64 else 1e-6)
+    # (no sampling pool here: 32 hidden one-lane qstates are 2^32 terms per entry in the reference's
+    #  prepareProbArray, CPUQubitsStatesGetter.cpp:179-247 — it segfaults on this case)
+    sim.terminate()
+
+
+def cases_rz_diag():
+    """the two diagonal entries of the reference's Rz(phi) as functions of phi (GateMatrix.cpp: Rz =
+    diag(e^{-i phi/2}, e^{i phi/2}))"""
+    return (lambda phi: np.exp(-0.5j * phi), lambda phi: np.exp(0.5j * phi))
+
+
+@pytest.mark.parametrize('dtype', (np.float64, np.float32))
+def test_more_than_40_separate_qregs(cuda_runtime, dtype):
+    _product_state_case(cuda_runtime, dtype)

@@ -156,3 +156,10 @@ def test_qft20_config0(golden, ref_runtime):
         assert cases.rel_err(sim.qubits.states[:512], golden['qft20/py/states_head']) < 1e-12
         assert cases.rel_err(sim.qubits.states[::4099],
                              golden['qft20/py/states_stride4099']) < 1e-12
+
+
+def test_more_than_40_separate_qregs_on_the_reference_runtime(ref_runtime):
+    """the same product-state case the GPU suite runs (tests/test_gpu_parity.py), on the reference CPU
+    runtime: pins the expectations of that test (Rz convention, index order, pool over a subset)"""
+    from tests.test_gpu_parity import _product_state_case
+    _product_state_case(ref_runtime.module, np.float64)
